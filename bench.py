@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""
+bench.py -- decode tok/s of the EXL3 qgemm hot path on Llama-3.1-8B shapes @ 4.0 bpw, batch 1 (BASELINE.json metric).
+
+A "step" is one token's worth of quantized GEMMs: 32 layers x (q, k, v, o, gate, up, down) + lm_head (K=6), m = 1,
+executed back to back over DISTINCT synthetic weight buffers (3.88 GB >> 126 MB L2, so nothing is cache-resident
+between steps).  Attention / norm / rope are not part of the hot path and are not executed.
+
+  value      tok/s with inputs resident in HBM when the timed region starts (CUDA-graph replay of the token)
+  e2e        same, through the reference-facing operator surface with HOST buffers: every step copies the token's
+             hidden state from pinned host memory, runs the token, and reads the lm_head logits back to the host
+  roofline   algorithmic bytes of the step (k*n*K/8 + 2mk + mn*{2|4} + 2(k+n) per GEMM) / step time,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline   the oracle port of the reference's torch dequant+matmul path (LinearEXL3.get_weight_tensor semantics)
+             timed on the host cores on a bounded sample (rank 0, N=1)
+
+N > 1 (torchrun): the same token, tensor-parallel: q/k/v/gate/up column-sharded, o/down row-sharded with one
+all-reduce (sum) per row-parallel output, lm_head column-sharded ("scaling": "strong").
+
+--impl reference: the CPU path only (the reference has no CPU qgemm: its torch dequant+matmul semantics restated
+in oracle/ are timed with all host threads), same metric/config, "impl": "reference".
+"""
+from __future__ import annotations
+import argparse, json, os, sys, time, subprocess, threading, statistics
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    "llama-3.1-8b": dict(hidden=4096, inter=14336, q=4096, kv=1024, layers=32, vocab=128256, K=4, head_K=6),
+    "llama-3.1-70b": dict(hidden=8192, inter=28672, q=8192, kv=1024, layers=80, vocab=128256, K=4, head_K=6),
+}
+
+
+def token_plan(cfg, tp=1):
+    """[(name, k, n, K, c_fp32, reduce)] per rank for one layer, + head.  Sharding as modules/quant/exl3.py:284-330."""
+    h, it, q, kv = cfg["hidden"], cfg["inter"], cfg["q"], cfg["kv"]
+    K = cfg["K"]
+    sh = lambda x: max(128, (x // tp) // 128 * 128) if tp > 1 else x
+    layer = [
+        ("q", h, sh(q), K, False, False), ("k", h, sh(kv), K, False, False), ("v", h, sh(kv), K, False, False),
+        ("o", sh(q), h, K, True, tp > 1),
+        ("gate", h, sh(it), K, True, False), ("up", h, sh(it), K, True, False),
+        ("down", sh(it), h, K, True, tp > 1),
+    ]
+    vs = cfg["vocab"] // 128 * 128
+    head = ("lm_head", h, sh(vs) if tp > 1 else vs, cfg["head_K"], True, False)
+    return layer, head
+
+
+def alg_bytes(m, k, n, K, c_fp32):
+    return k * n * K // 8 + 2 * m * k + m * n * (4 if c_fp32 else 2) + 2 * (k + n)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's torch dequant + matmul path)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def cpu_path_time(cfg, budget_s=20.0):
+    """
+    Reference semantics: W = get_weight_tensor() (decode -> H128 left -> *suh -> H128 right -> *svh, torch fp32
+    matmuls with the 128x128 Hadamard, modules/quant/exl3.py:227-237 + quantize.py:340-357), then x @ W in fp32.
+    Sample: as many whole matrices of layer 0 (q, k, v, o, gate, up, down order) as fit the time budget.
+    Returns (weights_per_second, cores, sample_description, (y, name, k, n) of the first matrix for validation).
+    """
+    import ctypes, numpy as np, torch
+    from oracle import exl3_oracle as orc
+    so = os.path.join(ROOT, "oracle", "libexl3oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libexl3oracle.so"])
+    lib = ctypes.CDLL(so)
+    lib.exl3o_reconstruct_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    layer, _ = token_plan(cfg, 1)
+    H = torch.from_numpy((orc.hadamard_matrix_128() / np.sqrt(128.0)).astype(np.float32))
+    done_w, t_total, names, first = 0, 0.0, [], None
+    for (name, k, n, K, c_fp32, _) in layer:
+        tr, suh, svh, x = orc.make_synthetic(k, n, K)
+        w = np.empty((k, n), dtype=np.float32)
+        t0 = time.perf_counter()
+        lib.exl3o_reconstruct_f32(w.ctypes.data, tr.ctypes.data, k, n, K, 2, cores)
+        wt = torch.from_numpy(w)
+        wt = (H @ wt.view(k // 128, 128, n)).view(k, n)
+        wt *= torch.from_numpy(suh.astype(np.float32)).unsqueeze(1)
+        wt = (wt.view(k, n // 128, 128) @ H).view(k, n)
+        wt *= torch.from_numpy(svh.astype(np.float32)).unsqueeze(0)
+        y = torch.from_numpy(x.astype(np.float32)) @ wt
+        dt = time.perf_counter() - t0
+        t_total += dt; done_w += k * n; names.append(name)
+        if first is None:
+            first = (y.numpy().copy(), name, k, n, K)
+        if t_total > budget_s:
+            break
+    return done_w / t_total, cores, f"layer-0 matrices {'+'.join(names)} ({done_w / 1e6:.1f} M weights, {t_total:.1f} s)", first
+
+
+def weights_per_token(cfg):
+    layer, head = token_plan(cfg, 1)
+    return cfg["layers"] * sum(k * n for (_, k, n, _, _, _) in layer) + head[1] * head[2]
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wps, cores, sample, _ = cpu_path_time(cfg, budget_s=10.0)   # warm-up / page-in
+    vals = []
+    for _ in range(max(1, args.steps)):
+        wps, cores, sample, _ = cpu_path_time(cfg, budget_s=min(20.0, 120.0 / max(1, args.steps)))
+        vals.append(wps / weights_per_token(cfg))
+    v = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": "decode tok/s Llama-3.1-8B 4.0bpw b=1 (qgemm path)", "value": v, "unit": "tok/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} EXL3 4.0bpw b=1 decode, qgemm path; CPU torch dequant+matmul "
+                               "(reference LinearEXL3.get_weight_tensor semantics, oracle port) on a bounded sample",
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+class Token:
+    """All quantized linears of one token for one TP rank, with their input/output/scratch buffers."""
+
+    def __init__(self, cfg, tp, rank, dev, seed=1234):
+        import torch
+        from exllamav3_b200 import ext
+        self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
+        g = torch.Generator(device=dev); g.manual_seed(seed + rank)
+        layer, head = token_plan(cfg, tp)
+        self.mats = []
+        self.alg_bytes = 0
+        plan = [(l, spec) for l in range(cfg["layers"]) for spec in layer] + [(-1, head)]
+        for (l, (name, k, n, K, c_fp32, red)) in plan:
+            tr = torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
+            sgn = lambda sz: (torch.randint(0, 2, (sz,), generator=g, device=dev) * 2 - 1).float()
+            suh = (sgn(k) * (0.5 + 1.5 * torch.rand(k, generator=g, device=dev)) / (k * tp) ** 0.5).half()
+            svh = (sgn(n) * (0.5 + 1.5 * torch.rand(n, generator=g, device=dev))).half()
+            x = torch.randn((1, k), generator=g, device=dev).half()
+            y = torch.empty((1, n), dtype=torch.float if c_fp32 else torch.half, device=dev)
+            xh = torch.empty((1, k), dtype=torch.half, device=dev)
+            self.mats.append(dict(name=name, layer=l, k=k, n=n, K=K, tr=tr, suh=suh, svh=svh, x=x, y=y, xh=xh,
+                                  c_fp32=c_fp32, reduce=red))
+            self.alg_bytes += alg_bytes(1, k, n, K, c_fp32)
+        self.first_x = self.mats[0]["x"]
+        self.logits = self.mats[-1]["y"]
+
+    def run(self):
+        ext, dist = self.ext, None
+        for mt in self.mats:
+            ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
+            if mt["reduce"]:
+                import torch.distributed as dist
+                dist.all_reduce(mt["y"])
+
+
+def run_gpu_arm(args, cfg):
+    import torch
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the EXL3 path has no CPU implementation (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from exllamav3_b200 import ext
+
+    tok = Token(cfg, world, rank, dev)
+    stream = torch.cuda.Stream(device=dev)
+    launches0 = ext.launch_count()
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            tok.run()                       # eager warm-up: lazy context init, NCCL channels
+    stream.synchronize()
+    launches_per_step = (ext.launch_count() - launches0) // 2
+
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                tok.run()
+        except Exception as e:                # capture unsupported (e.g. NCCL config): eager launches
+            if rank == 0:
+                print(f"# graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            tok.run()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+
+    # ---- end-to-end through the operator surface with host buffers ----
+    hx = torch.randn((1, cfg["hidden"])).half().pin_memory()
+    hlogits = torch.empty(tuple(tok.logits.shape), dtype=tok.logits.dtype).pin_memory()
+
+    def e2e_step():
+        tok.first_x.copy_(hx, non_blocking=True)
+        step()
+        hlogits.copy_(tok.logits, non_blocking=True)
+        stream.synchronize()                 # the host consumes the logits every token
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps     # events bracket the loop; host round trips are inside
+
+    peak, peak_src = read_peaks()
+    achieved = tok.alg_bytes / (ms_per_step * 1e-3) / 1e9          # per rank (each rank streams its own shard)
+    cpu_baseline = None
+    check = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wps, cores, sample, first = cpu_path_time(cfg, budget_s=args.cpu_budget)
+        cpu_baseline = {"value": wps / weights_per_token(cfg), "unit": "tok/s", "cores": cores, "kind": "port",
+                        "sample": sample}
+        # validate the GPU path on the same matrix the CPU arm just computed (oracle as checker only)
+        import numpy as np
+        from oracle import exl3_oracle as orc
+        y_cpu, name, k, n, K = first
+        tr, suh, svh, x = orc.make_synthetic(k, n, K)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        C = torch.empty((1, n), dtype=torch.float, device=dev)
+        ext.exl3_gemm(T(x), T(tr), C, T(suh), torch.empty((1, k), dtype=torch.half, device=dev), T(svh), -1, False, True, 0)
+        err = float(np.abs(C.cpu().numpy() - y_cpu).max() / np.abs(y_cpu).max())
+        check = {"matrix": name, "max_rel_err_vs_cpu_path": err}
+        assert err < 1e-2, f"GPU result deviates from the CPU path: {err}"
+
+    if rank == 0:
+        line = {
+            "metric": "decode tok/s Llama-3.1-8B 4.0bpw b=1 (qgemm path)", "value": 1000.0 / ms_per_step, "unit": "tok/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"{args.model} EXL3 4.0bpw (lm_head 6bpw) b=1 decode: "
+                                   f"{len(tok.mats)} qgemms/token, m=1, mul1 codebook, random-init trellis",
+                       "parallelism": f"tp{world}" if world > 1 else "single",
+                       "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
+                       "cuda_graph": graph is not None},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes of the whole step / step time (all launches incl. input transforms)"},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "tok/s", "h2d_bytes_per_step": hx.numel() * 2,
+                    "d2h_bytes_per_step": hlogits.numel() * hlogits.element_size()},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "check": check,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3.1-8b", choices=list(MODELS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    cfg = MODELS[args.model]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_gpu_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,258 @@
+// C ABI of libexl3b200.so (declared in include/exl3b200.h): argument validation mirroring the reference's
+// TORCH_CHECKs, per-device context, kernel-path selection.  No torch types, no CPU fallback.
+#include "common.cuh"
+#include "epilogue.cuh"
+#include <mutex>
+#include <string>
+#include <atomic>
+#include <cstring>
+
+namespace exl3b {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_force_path{0};
+
+void set_error(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+}
+
+int fail(int status, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+    return -status;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static constexpr int MAX_DEVICES = 32;
+static DevCtx g_ctx[MAX_DEVICES];
+static std::mutex g_ctx_mutex;
+
+int get_ctx(DevCtx** out)
+{
+    int dev = -1;
+    EXL3B_CUDA(cudaGetDevice(&dev));
+    EXL3B_CHECK(dev >= 0 && dev < MAX_DEVICES, EXL3B_ERR_CUDA, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    DevCtx& c = g_ctx[dev];
+    if (c.device < 0)
+    {
+        cudaDeviceProp prop;
+        EXL3B_CUDA(cudaGetDeviceProperties(&prop, dev));
+        EXL3B_CHECK(prop.major == 10, EXL3B_ERR_CUDA,
+                    "exl3b200 is built for sm_100a only; device %d is sm_%d%d (no fallback path exists)",
+                    dev, prop.major, prop.minor);
+        c.num_sms = prop.multiProcessorCount;
+        c.cc = prop.major * 10 + prop.minor;
+        EXL3B_CUDA(cudaMalloc(&c.ws, DevCtx::NUM_SLOTS * DevCtx::WS_BYTES_PER_SLOT));
+        EXL3B_CUDA(cudaMalloc(&c.counters, sizeof(int) * DevCtx::NUM_SLOTS * DevCtx::COUNTERS_PER_SLOT));
+        EXL3B_CUDA(cudaMemset(c.counters, 0, sizeof(int) * DevCtx::NUM_SLOTS * DevCtx::COUNTERS_PER_SLOT));
+        EXL3B_CUDA(cudaMalloc(&c.tabs, sizeof(MSlotTable) * DevCtx::NUM_SLOTS));
+        EXL3B_CUDA(cudaDeviceSynchronize());
+        c.device = dev;
+    }
+    *out = &c;
+    return 0;
+}
+
+int ensure_xh_scratch(DevCtx* ctx, size_t elems)
+{
+    if (ctx->xh_scratch_elems >= elems) return 0;
+    // growing is rare (first call / larger m); synchronise so no in-flight kernel still reads the old buffer
+    EXL3B_CUDA(cudaDeviceSynchronize());
+    if (ctx->xh_scratch) cudaFree(ctx->xh_scratch);
+    size_t want = elems < (1u << 20) ? (1u << 20) : elems;
+    EXL3B_CUDA(cudaMalloc(&ctx->xh_scratch, want * sizeof(half)));
+    ctx->xh_scratch_elems = want;
+    return 0;
+}
+
+}  // namespace exl3b
+
+using namespace exl3b;
+
+extern "C" {
+
+int exl3b_abi_version(void) { return EXL3B_ABI_VERSION; }
+
+const char* exl3b_last_error(void) { return g_err.c_str(); }
+
+int64_t exl3b_launch_count(void) { return g_launches.load(); }
+
+int exl3b_set_gemm_path(int tag) { return g_force_path.exchange(tag); }
+
+int exl3b_num_sms(int device)
+{
+    cudaDeviceProp prop;
+    EXL3B_CUDA(cudaGetDeviceProperties(&prop, device));
+    return prop.multiProcessorCount;
+}
+
+int exl3b_cc(int device)
+{
+    cudaDeviceProp prop;
+    EXL3B_CUDA(cudaGetDeviceProperties(&prop, device));
+    return prop.major * 10 + prop.minor;
+}
+
+static int check_kcb(int K, int cb)
+{
+    EXL3B_CHECK(K >= 1 && K <= 8, EXL3B_ERR_ARG, "K must be 1..8, got %d", K);
+    EXL3B_CHECK(cb >= 0 && cb <= 2, EXL3B_ERR_ARG, "cb must be 0 (3inst), 1 (mcg) or 2 (mul1), got %d", cb);
+    return 0;
+}
+
+int exl3b_had_r_128(void* stream, const void* in, void* out, const void* pre_scale, const void* post_scale,
+                    float scale, int rows, int cols, int is_fp32)
+{
+    EXL3B_CHECK(rows >= 0 && cols >= 0, EXL3B_ERR_SHAPE, "had_r_128: negative size");
+    EXL3B_CHECK(cols % 128 == 0, EXL3B_ERR_SHAPE, "had_r_128: dim 1 (%d) must be divisible by 128", cols);
+    if (rows == 0 || cols == 0) return 0;
+    EXL3B_CHECK(in && out, EXL3B_ERR_ARG, "had_r_128: null tensor");
+    DevCtx* ctx; int r = get_ctx(&ctx); if (r) return r;
+    return launch_had_r_128((cudaStream_t) stream, in, out, (const half*) pre_scale, (const half*) post_scale,
+                            scale, rows, cols, is_fp32 != 0);
+}
+
+int exl3b_reconstruct(void* stream, void* unpacked, const void* packed, int k, int n_out, int packed_tiles_n,
+                      int K, int cb, int64_t n_offset)
+{
+    int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(k >= 0 && k % 16 == 0, EXL3B_ERR_SHAPE, "reconstruct: K dimension (%d) must be divisible by 16", k);
+    if (k == 0 || n_out == 0) return 0;
+    EXL3B_CHECK(n_out % 128 == 0, EXL3B_ERR_SHAPE, "unpacked N dimension must be divisible by 128");
+    EXL3B_CHECK(n_offset % 128 == 0, EXL3B_ERR_SHAPE, "n_offset must be divisible by 128");
+    EXL3B_CHECK(n_offset >= 0, EXL3B_ERR_SHAPE, "n_offset must be non-negative");
+    EXL3B_CHECK(n_offset + n_out <= (int64_t) packed_tiles_n * 16, EXL3B_ERR_SHAPE,
+                "reconstruct slice exceeds packed tensor bounds");
+    EXL3B_CHECK(unpacked && packed, EXL3B_ERR_ARG, "reconstruct: null tensor");
+    DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+    return launch_reconstruct((cudaStream_t) stream, (half*) unpacked, (const uint16_t*) packed, k, n_out,
+                              packed_tiles_n, K, cb, n_offset);
+}
+
+int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed, const void* suh, const void* svh,
+                          int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset)
+{
+    int r = check_kcb(K, cb); if (r) return r;
+    if (k == 0 || n_out == 0) return 0;
+    EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "reconstruct_had: K dimension must be divisible by 128");
+    EXL3B_CHECK(n_out % 128 == 0, EXL3B_ERR_SHAPE, "reconstruct_had: N dimension must be divisible by 128");
+    EXL3B_CHECK(n_offset % 128 == 0, EXL3B_ERR_SHAPE, "n_offset must be divisible by 128");
+    EXL3B_CHECK(n_offset >= 0, EXL3B_ERR_SHAPE, "n_offset must be non-negative");
+    EXL3B_CHECK(n_offset + n_out <= (int64_t) packed_tiles_n * 16, EXL3B_ERR_SHAPE,
+                "reconstruct slice exceeds packed tensor bounds");
+    EXL3B_CHECK(unpacked && packed && suh && svh, EXL3B_ERR_ARG, "reconstruct_had: null tensor");
+    DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+    return launch_reconstruct_had((cudaStream_t) stream, (half*) unpacked, (const uint16_t*) packed,
+                                  (const half*) suh, (const half*) svh, k, n_out, packed_tiles_n, K, cb, n_offset);
+}
+
+int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void* suh, void* A_had, const void* svh,
+               int m, int k, int n, int K, int cb, int c_fp32, int force_shape_idx, int force_num_sms)
+{
+    (void) force_shape_idx;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(m >= 0 && k >= 0 && n >= 0, EXL3B_ERR_SHAPE, "exl3_gemm: negative size");
+    EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: k (%d) must be divisible by 128", k);
+    EXL3B_CHECK(n % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: n (%d) must be divisible by 128", n);
+    if (m == 0 || n == 0) return EXL3B_TAG_NOP;
+    EXL3B_CHECK(A && B && C, EXL3B_ERR_ARG, "exl3_gemm: null tensor");
+    DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+
+    const half* xh = (const half*) A;
+    if (suh && k > 0)
+    {
+        half* dst = (half*) A_had;
+        if (!dst)
+        {
+            r = ensure_xh_scratch(ctx, (size_t) m * k); if (r) return r;
+            dst = ctx->xh_scratch;
+        }
+        r = launch_had_r_128(stream, A, dst, (const half*) suh, nullptr, 1.0f, m, k, false); if (r) return r;
+        xh = dst;
+    }
+
+    GemmArgs g{};
+    g.xh = xh; g.B = (const uint32_t*) B; g.C = C; g.svh = (const half*) svh;
+    g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f;
+    g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
+
+    int path = g_force_path.load();
+    if (path == EXL3B_TAG_TC)
+        EXL3B_CHECK(gemm_tc_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: tcgen05 path forced but shape unsupported");
+    if (path != EXL3B_TAG_SIMT && gemm_tc_supported(g))
+        return launch_gemm_tc(stream, ctx, g);
+    return launch_gemm_simt(stream, ctx, g);
+}
+
+int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, const uint64_t* suh_ptrs, void* A_had,
+                const uint64_t* svh_ptrs, const int64_t* indices, int num_indices, const void* weights,
+                int bszm_in, int bszm_out, int m, int k, int n, int K, int cb, int c_fp32,
+                int min_index, int max_index, int num_tokens,
+                const int32_t* size_n_list, const uint64_t* c_ptrs, int num_c_ptrs,
+                int force_shape_idx, int force_num_sms)
+{
+    (void) force_shape_idx; (void) force_num_sms;
+    int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(num_tokens == 1 || min_index < 0, EXL3B_ERR_ARG,
+                "exl3_mgemm: multi-token reduction (num_tokens > 1) is not compatible with expert-range "
+                "filtering (min_index >= 0); TP-sharded experts must use num_tokens == 1");
+    EXL3B_CHECK(num_tokens >= 1, EXL3B_ERR_ARG, "exl3_mgemm: num_tokens must be >= 1");
+    EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "exl3_mgemm: k (%d) must be divisible by 128", k);
+    EXL3B_CHECK(n % 128 == 0, EXL3B_ERR_SHAPE, "exl3_mgemm: n (%d) must be divisible by 128", n);
+    if (size_n_list)
+    {
+        EXL3B_CHECK(c_ptrs, EXL3B_ERR_ARG, "exl3_mgemm: size_n_list requires c_ptrs");
+        EXL3B_CHECK(num_tokens == 1 && min_index < 0 && !weights, EXL3B_ERR_ARG,
+                    "exl3_mgemm: per-matrix widths incompatible with multi-token/filtering/weights");
+        bszm_out = num_c_ptrs;
+    }
+    EXL3B_CHECK(min_index < 0 || indices, EXL3B_ERR_ARG, "exl3_mgemm: expert-range filtering requires indices");
+    EXL3B_CHECK(!weights || indices, EXL3B_ERR_ARG, "exl3_mgemm: weights require indices");
+    if (indices)
+        EXL3B_CHECK(num_indices <= bszm_in || num_indices <= bszm_out, EXL3B_ERR_SHAPE,
+                    "mgemm: too many indices for tensor batch");
+    EXL3B_CHECK(A && B_ptrs && C && suh_ptrs && A_had && svh_ptrs, EXL3B_ERR_ARG, "exl3_mgemm: null tensor");
+    DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+    MGemmArgs a{};
+    a.A = (const half*) A; a.B_ptrs = B_ptrs; a.C = C; a.suh_ptrs = suh_ptrs; a.A_had = (half*) A_had;
+    a.svh_ptrs = svh_ptrs; a.indices = indices; a.num_indices = num_indices; a.weights = (const half*) weights;
+    a.bszm_in = bszm_in; a.bszm_out = bszm_out; a.m = m; a.k = k; a.n = n; a.K = K; a.cb = cb;
+    a.c_fp32 = c_fp32 != 0; a.min_index = min_index; a.max_index = max_index; a.num_tokens = num_tokens;
+    a.size_n_list = size_n_list; a.c_ptrs = c_ptrs; a.num_c_ptrs = num_c_ptrs;
+    return launch_mgemm((cudaStream_t) stream, ctx, a);
+}
+
+int exl3b_hgemm(void* stream, const void* a, const void* b, void* c, int m, int k, int n, int c_fp32,
+                int64_t c_stride)
+{
+    EXL3B_CHECK(m >= 0 && k >= 0 && n >= 0, EXL3B_ERR_SHAPE, "hgemm: negative size");
+    if (m == 0 || n == 0) return 0;
+    EXL3B_CHECK(a && b && c, EXL3B_ERR_ARG, "hgemm: null tensor");
+    EXL3B_CHECK(c_stride >= n, EXL3B_ERR_SHAPE, "c row stride is too small");
+    DevCtx* ctx; int r = get_ctx(&ctx); if (r) return r;
+    return launch_hgemm((cudaStream_t) stream, (const half*) a, (const half*) b, c, m, k, n, c_fp32 != 0, c_stride);
+}
+
+int exl3b_gemm_host(void* stream_, const void* A_host, void* C_host, void* d_A, void* d_C, void* d_A_had,
+                    const void* B, const void* suh, const void* svh, int m, int k, int n, int K, int cb, int c_fp32)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    EXL3B_CHECK(A_host && C_host && d_A && d_C, EXL3B_ERR_ARG, "exl3_gemm_host: null buffer");
+    EXL3B_CUDA(cudaMemcpyAsync(d_A, A_host, (size_t) m * k * sizeof(half), cudaMemcpyHostToDevice, stream));
+    int r = exl3b_gemm(stream_, d_A, B, d_C, suh, d_A_had, svh, m, k, n, K, cb, c_fp32, -1, 0);
+    if (r < 0) return r;
+    EXL3B_CUDA(cudaMemcpyAsync(C_host, d_C, (size_t) m * n * (c_fp32 ? 4 : 2), cudaMemcpyDeviceToHost, stream));
+    EXL3B_CUDA(cudaStreamSynchronize(stream));
+    return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Shared host/device helpers for the exl3b200 library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/exl3b200.h"
+
+namespace exl3b {
+
+constexpr float R_SCALE = 0.088388347648f;      // 1/sqrt(128), same literal as the reference (hadamard.cu:112)
+
+// ---- error plumbing ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+#define EXL3B_CHECK(cond, status, ...) do { if (!(cond)) return ::exl3b::fail(status, __VA_ARGS__); } while (0)
+#define EXL3B_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return ::exl3b::fail(EXL3B_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
+
+void count_launch(int n = 1);
+
+// Per-launch table of active matrix slots for mgemm (device memory, owned by DevCtx).
+struct MSlotTable
+{
+    static constexpr int MAX_SLOTS = 128;       // same capacity as the reference's v_indices (exl3_gemm_kernel.cuh:82-85)
+    int n_active;
+    int mat[MAX_SLOTS];
+    half weight[MAX_SLOTS];
+};
+
+// ---- per-device context -----------------------------------------------------------------------------------
+// Split-K partial sums and tile counters.  Launches rotate through NUM_SLOTS independent regions so that
+// consecutive (PDL-overlapped) launches on one stream never share counters; counters are self-resetting.
+struct DevCtx
+{
+    static constexpr int NUM_SLOTS = 8;
+    static constexpr size_t WS_BYTES_PER_SLOT = 8u << 20;     // fp32 partials
+    static constexpr int COUNTERS_PER_SLOT = 32768;
+    int device = -1;
+    int num_sms = 0;
+    int cc = 0;
+    float* ws = nullptr;          // NUM_SLOTS * WS_BYTES_PER_SLOT
+    int* counters = nullptr;      // NUM_SLOTS * COUNTERS_PER_SLOT, zero-initialised once
+    MSlotTable* tabs = nullptr;   // NUM_SLOTS mgemm slot tables
+    half* xh_scratch = nullptr;   // input-transform scratch when the caller passes A_had = NULL
+    size_t xh_scratch_elems = 0;
+    uint64_t launch_seq = 0;
+    int next_slot() { return (int) (launch_seq++ % NUM_SLOTS); }
+    float* ws_slot(int s) { return (float*) ((char*) ws + (size_t) s * WS_BYTES_PER_SLOT); }
+    int* counter_slot(int s) { return counters + (size_t) s * COUNTERS_PER_SLOT; }
+    MSlotTable* tab_slot(int s) { return tabs + s; }
+};
+int get_ctx(DevCtx** out);       // context of the current device (lazy init), status code
+int ensure_xh_scratch(DevCtx* ctx, size_t elems);
+
+// ---- launchers implemented in the .cu files ------------------------------------------------------------------
+int launch_had_r_128(cudaStream_t stream, const void* in, void* out, const half* pre, const half* post,
+                     float scale, int rows, int cols, bool fp32);
+int launch_reconstruct(cudaStream_t stream, half* unpacked, const uint16_t* packed, int k, int n_out,
+                       int packed_tiles_n, int K, int cb, int64_t n_offset);
+int launch_reconstruct_had(cudaStream_t stream, half* unpacked, const uint16_t* packed, const half* suh,
+                           const half* svh, int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset);
+
+struct GemmArgs
+{
+    const half* xh;          // transformed input (m, k) [or raw A when no input transform]
+    const uint32_t* B;
+    void* C;
+    const half* svh;         // may be null
+    int m, k, n, K, cb;
+    bool c_fp32;
+    float out_scale;         // extra factor folded into the output transform (mgemm weights), 1.0f otherwise
+    int max_ctas;            // 0 = all SMs
+};
+int launch_gemm_simt(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+bool gemm_tc_supported(const GemmArgs& a);
+
+struct MGemmArgs
+{
+    const half* A; const uint64_t* B_ptrs; void* C; const uint64_t* suh_ptrs; half* A_had; const uint64_t* svh_ptrs;
+    const int64_t* indices; int num_indices; const half* weights;
+    int bszm_in, bszm_out, m, k, n, K, cb; bool c_fp32;
+    int min_index, max_index, num_tokens;
+    const int32_t* size_n_list; const uint64_t* c_ptrs; int num_c_ptrs;
+};
+int launch_mgemm(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
+
+int launch_hgemm(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,
+                 int64_t c_stride);
+
+// ---- (K, cb) template dispatch ---------------------------------------------------------------------------------
+#define EXL3B_DISPATCH_K_CB(FN, K, cb, ...)                                                        \
+    do { switch ((cb) * 8 + (K) - 1) {                                                             \
+        case  0: FN<1, 0>(__VA_ARGS__); break; case  1: FN<2, 0>(__VA_ARGS__); break;              \
+        case  2: FN<3, 0>(__VA_ARGS__); break; case  3: FN<4, 0>(__VA_ARGS__); break;              \
+        case  4: FN<5, 0>(__VA_ARGS__); break; case  5: FN<6, 0>(__VA_ARGS__); break;              \
+        case  6: FN<7, 0>(__VA_ARGS__); break; case  7: FN<8, 0>(__VA_ARGS__); break;              \
+        case  8: FN<1, 1>(__VA_ARGS__); break; case  9: FN<2, 1>(__VA_ARGS__); break;              \
+        case 10: FN<3, 1>(__VA_ARGS__); break; case 11: FN<4, 1>(__VA_ARGS__); break;              \
+        case 12: FN<5, 1>(__VA_ARGS__); break; case 13: FN<6, 1>(__VA_ARGS__); break;              \
+        case 14: FN<7, 1>(__VA_ARGS__); break; case 15: FN<8, 1>(__VA_ARGS__); break;              \
+        case 16: FN<1, 2>(__VA_ARGS__); break; case 17: FN<2, 2>(__VA_ARGS__); break;              \
+        case 18: FN<3, 2>(__VA_ARGS__); break; case 19: FN<4, 2>(__VA_ARGS__); break;              \
+        case 20: FN<5, 2>(__VA_ARGS__); break; case 21: FN<6, 2>(__VA_ARGS__); break;              \
+        case 22: FN<7, 2>(__VA_ARGS__); break; case 23: FN<8, 2>(__VA_ARGS__); break;              \
+    } } while (0)
+
+// ---- device helpers -----------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// 128-point Sylvester Hadamard across one warp, 4 consecutive elements per lane, fp32.  Performs exactly the
+// additions of the reference's had_*_r_128_inner (hadamard_inner.cuh:118-131, 14-41): in-lane 4-point, then
+// xor-shuffle stages 1..16 with new = (lane & i ? -own : own) + partner.
+__device__ __forceinline__ void had128_warp(float& h0, float& h1, float& h2, float& h3, int lane)
+{
+    float s0 = h0 + h1, d0 = h0 - h1, s1 = h2 + h3, d1 = h2 - h3;
+    h0 = s0 + s1; h1 = d0 + d1; h2 = s0 - s1; h3 = d0 - d1;
+    #pragma unroll
+    for (int i = 1; i < 32; i <<= 1)
+    {
+        float p0 = __shfl_xor_sync(0xffffffffu, h0, i);
+        float p1 = __shfl_xor_sync(0xffffffffu, h1, i);
+        float p2 = __shfl_xor_sync(0xffffffffu, h2, i);
+        float p3 = __shfl_xor_sync(0xffffffffu, h3, i);
+        bool neg = (lane & i) != 0;
+        h0 = (neg ? -h0 : h0) + p0;
+        h1 = (neg ? -h1 : h1) + p1;
+        h2 = (neg ? -h2 : h2) + p2;
+        h3 = (neg ? -h3 : h3) + p3;
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(half a, half b)
+{
+    return (uint32_t) __half_as_ushort(a) | ((uint32_t) __half_as_ushort(b) << 16);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace exl3b

@@ -1,0 +1,133 @@
+// EXL3 trellis decode primitives for sm_100a.
+//
+// Format facts (reference: exllamav3_ext/quant/exl3_dq.cuh:15-31, codebook.cuh:56-90, pack.cu:9-57,
+// modules/quant/exl3_lib/quantize.py:22-44):
+//   * a 16x16 tile is 256*K bits = 8K little-endian uint32 words; word w holds stream bits [32w, 32w+32) MSB first
+//   * the 16-bit state of position t is the window ending at stream bit (t+1)*K, wrapping modulo 256*K
+//   * position t = 8*l + i  (l = 0..31, i = 0..7) sits at  k = 2*(l%4) + (i&1) + 8*((i>>1)&1),  n = l/4 + 8*(i>>2)
+//
+// Work decomposition used by every kernel in this library (different from the reference's mma.sync fragment order):
+//   a tile is cut into 8 "chunks" c = 0..7 of 32 positions (K words).  Chunk c holds tile columns n = c (positions
+//   with i < 4, "half 0") and n = c + 8 (i >= 4, "half 1"), all 16 k-rows each.  One thread decodes one
+//   (chunk, half) = ONE tile column x 16 k-values from K+1 words (the chunk plus the preceding word), with every
+//   bit offset a compile-time constant.  `half` is warp-uniform in all kernels, so there is no divergence.
+//
+//   Output order matches what a tcgen05 K-major operand row wants: out[j] = packed fp16 pair (k = 2j, 2j+1).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace exl3b {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lop3_and_xor(uint32_t x, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(r) : "r"(x), "r"(b), "r"(c));   // (x & b) ^ c
+    return r;
+}
+
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Two 16-bit states -> packed fp16x2 (lo = value(s0), hi = value(s1)), bit-exact with the reference's
+// decode_3inst_2<cb> (codebook.cuh:92-123).
+template <int cb>
+__device__ __forceinline__ uint32_t decode_pair(uint32_t s0, uint32_t s1)
+{
+    if constexpr (cb == 0)
+    {
+        uint32_t x0 = s0 * 89226354u + 64248484u;
+        uint32_t x1 = s1 * 89226354u + 64248484u;
+        x0 = lop3_and_xor(x0, 0x8fff8fffu, 0x3b603b60u);
+        x1 = lop3_and_xor(x1, 0x8fff8fffu, 0x3b603b60u);
+        return hadd2_u32(prmt(x0, x1, 0x5410), prmt(x0, x1, 0x7632));
+    }
+    else if constexpr (cb == 1)
+    {
+        uint32_t x0 = s0 * 0xCBAC1FEDu;
+        uint32_t x1 = s1 * 0xCBAC1FEDu;
+        x0 = lop3_and_xor(x0, 0x8fff8fffu, 0x3b603b60u);
+        x1 = lop3_and_xor(x1, 0x8fff8fffu, 0x3b603b60u);
+        return hadd2_u32(prmt(x0, x1, 0x5410), prmt(x0, x1, 0x7632));
+    }
+    else
+    {
+        uint32_t x0 = s0 * 0x83DCD12Du;
+        uint32_t x1 = s1 * 0x83DCD12Du;
+        uint32_t h0 = __dp4a(x0, 0x01010101u, 0x6400u);          // fp16 bits of (1024 + bytesum), exact
+        uint32_t h1 = __dp4a(x1, 0x01010101u, 0x6400u);
+        return hfma2_u32(prmt(h0, h1, 0x5410), 0x1eee1eeeu, 0xc931c931u);
+    }
+}
+
+// state of the position whose window ends at chunk-relative stream bit E (K <= E <= 32K); w[0] = word preceding
+// the chunk, w[1..K] = chunk words.  All indices/shifts are compile-time.
+template <int K, int E>
+__device__ __forceinline__ uint32_t window16(const uint32_t (&w)[K + 1])
+{
+    constexpr int wi = (E - 1) / 32;            // chunk word holding the last bit
+    constexpr int sh = (wi + 1) * 32 - E;       // 0..31
+    uint32_t v;
+    if constexpr (sh == 0)       v = w[1 + wi];
+    else if constexpr (sh <= 16) v = w[1 + wi] >> sh;            // window entirely inside one word
+    else                         v = __funnelshift_r(w[1 + wi], w[wi], sh);
+    return v & 0xffffu;
+}
+
+template <int K, int cb, int HALF, int J>
+__device__ __forceinline__ void decode4(const uint32_t (&w)[K + 1], uint32_t& lo_pair, uint32_t& hi_pair)
+{
+    // positions 8*J + 4*HALF + {0,1,2,3} of the chunk -> k = 2J, 2J+1 (lo_pair) and 2J+8, 2J+9 (hi_pair)
+    constexpr int P = 8 * J + 4 * HALF;
+    uint32_t s0 = window16<K, (P + 1) * K>(w);
+    uint32_t s1 = window16<K, (P + 2) * K>(w);
+    uint32_t s2 = window16<K, (P + 3) * K>(w);
+    uint32_t s3 = window16<K, (P + 4) * K>(w);
+    lo_pair = decode_pair<cb>(s0, s1);
+    hi_pair = decode_pair<cb>(s2, s3);
+}
+
+// One tile column (16 k-values) from K+1 words.  out[j] = fp16x2 (k = 2j, 2j+1), j = 0..7.
+template <int K, int cb, int HALF>
+__device__ __forceinline__ void decode16(const uint32_t (&w)[K + 1], uint32_t (&out)[8])
+{
+    decode4<K, cb, HALF, 0>(w, out[0], out[4]);
+    decode4<K, cb, HALF, 1>(w, out[1], out[5]);
+    decode4<K, cb, HALF, 2>(w, out[2], out[6]);
+    decode4<K, cb, HALF, 3>(w, out[3], out[7]);
+}
+
+// Thread -> column mapping inside a 128-column strip (8 tiles).  q = lane quarter (warp index % 4), i = lane.
+//   tile-in-strip = 4*(q>>1) + (i>>3), chunk = i&7, half = q&1   =>   n_local = 16*tile + 8*half + chunk
+__device__ __forceinline__ int strip_tile(int q, int i)  { return 4 * (q >> 1) + (i >> 3); }
+__device__ __forceinline__ int strip_col(int q, int i)   { return 16 * strip_tile(q, i) + 8 * (q & 1) + (i & 7); }
+
+// Load the K+1 words of (tile, chunk) from a tile base pointer (global or shared), 8K words per tile.
+template <int K>
+__device__ __forceinline__ void load_chunk(const uint32_t* tile, int chunk, uint32_t (&w)[K + 1])
+{
+    const uint32_t* p = tile + chunk * K;
+    w[0] = tile[chunk == 0 ? 8 * K - 1 : chunk * K - 1];
+    #pragma unroll
+    for (int j = 0; j < K; ++j) w[1 + j] = p[j];
+}
+
+}  // namespace exl3b

@@ -1,0 +1,301 @@
+"""
+Host-side mirror of the reference's `exllamav3_ext` operator surface for the EXL3 qgemm path, implemented over the
+C ABI of libexl3b200.so (include/exl3b200.h) with ctypes.  Same names, argument order, argument meaning and error
+behaviour (RuntimeError for shape/dtype violations) as the pybind11 bindings they replace:
+
+    exl3_gemm, exl3_mgemm                      exllamav3_ext/bindings.cpp:126,146
+    reconstruct, reconstruct_slice, reconstruct_had_slice      bindings.cpp:122-124
+    had_r_128, hgemm                           bindings.cpp:125,147
+    BC_LinearEXL3                              exllamav3_ext/libtorch/linear_bc.h:13-35, linear.cpp:34-71
+    g_get_cc, g_get_num_sms, exl3_gemm_num_kernel_shapes, exl3_gemm_shape_compat     bindings.cpp:127-131
+
+PyTorch is plumbing only here: device memory, the current CUDA stream and the device guard.
+There is no CPU or torch fallback: if the shared library is missing this module fails to import, and every op
+raises RuntimeError when given a non-CUDA tensor.
+"""
+from __future__ import annotations
+import ctypes, os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libexl3b200.so")
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} not found: build it with `python -m exllamav3_b200.build` "
+        "(the EXL3 path has no fallback implementation)")
+
+_lib = ctypes.CDLL(_LIB_PATH)
+
+_vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+_lib.exl3b_abi_version.restype = _i
+_lib.exl3b_last_error.restype = ctypes.c_char_p
+_lib.exl3b_launch_count.restype = _i64
+_lib.exl3b_num_sms.argtypes = [_i]; _lib.exl3b_num_sms.restype = _i
+_lib.exl3b_cc.argtypes = [_i]; _lib.exl3b_cc.restype = _i
+_lib.exl3b_set_gemm_path.argtypes = [_i]; _lib.exl3b_set_gemm_path.restype = _i
+_lib.exl3b_gemm.argtypes = [_vp] * 7 + [_i] * 8
+_lib.exl3b_gemm.restype = _i
+_lib.exl3b_mgemm.argtypes = [_vp] * 8 + [_i, _vp] + [_i] * 11 + [_vp, _vp] + [_i] * 3
+_lib.exl3b_mgemm.restype = _i
+_lib.exl3b_reconstruct.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64]
+_lib.exl3b_reconstruct.restype = _i
+_lib.exl3b_reconstruct_had.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64]
+_lib.exl3b_reconstruct_had.restype = _i
+_lib.exl3b_had_r_128.argtypes = [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i]
+_lib.exl3b_had_r_128.restype = _i
+_lib.exl3b_hgemm.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64]
+_lib.exl3b_hgemm.restype = _i
+_lib.exl3b_gemm_host.argtypes = [_vp] * 9 + [_i] * 6
+_lib.exl3b_gemm_host.restype = _i
+
+assert _lib.exl3b_abi_version() == 1
+
+EXL3B_TAG_SIMT = 100
+EXL3B_TAG_TC = 200
+
+lib = _lib      # raw handle for bench.py / tests (symbol export checks)
+lib_path = _LIB_PATH
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise RuntimeError(_lib.exl3b_last_error().decode())
+    return rc
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("exllamav3_b200: tensor is not on a CUDA device (no CPU path exists)")
+
+
+def _cb(mcg, mul1) -> int:
+    mcg, mul1 = bool(mcg), bool(mul1)
+    if mcg and mul1:
+        raise RuntimeError("Specified both mcg and mul1")
+    return 1 if mcg else (2 if mul1 else 0)
+
+
+def _dtype(t, dt, name):
+    if t.dtype != dt:
+        raise RuntimeError(f"{name} is incorrect datatype, must be {dt}")
+
+
+def launch_count() -> int:
+    return int(_lib.exl3b_launch_count())
+
+
+def set_gemm_path(tag: int) -> int:
+    """0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC.  Returns the previous setting."""
+    return int(_lib.exl3b_set_gemm_path(int(tag)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------------------------
+
+def exl3_gemm(A, B, C, suh, A_had, svh, force_shape_idx: int, mcg, mul1, force_num_sms: int) -> int:
+    """A @ B -> C with EXL3-quantized B.  exllamav3_ext/quant/exl3_gemm.cu:110-339."""
+    _need_cuda(A, B, C, suh, A_had, svh)
+    if B.dim() != 3:
+        raise RuntimeError("B: incorrect number of dimensions, must be 3")
+    _dtype(A, torch.half, "A")
+    _dtype(B, torch.int16, "B")
+    c_fp32 = C.dtype == torch.float
+    if not c_fp32:
+        _dtype(C, torch.half, "C")
+    size_k = A.shape[-1]
+    size_m = A.numel() // size_k if size_k else 0
+    size_n = B.shape[1] * 16
+    if size_k != B.shape[0] * 16:
+        raise RuntimeError("A and B incompatible shapes")
+    if C.shape[-1] != size_n:
+        raise RuntimeError("C and B incompatible shapes")
+    K = B.shape[2] // 16
+    assert A.is_contiguous() and B.is_contiguous() and C.is_contiguous()
+    with torch.cuda.device(A.device):
+        return _check(_lib.exl3b_gemm(
+            _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had) if suh is not None else None, _ptr(svh),
+            size_m, size_k, size_n, K, _cb(mcg, mul1), int(c_fp32), int(force_shape_idx), int(force_num_sms)))
+
+
+def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_idx: int, mcg, mul1,
+               min_index: int, max_index: int, force_num_sms: int, num_tokens: int = 1,
+               size_n_list=None, c_ptrs=None) -> int:
+    """Multi-matrix EXL3 GEMM over pointer tables.  exllamav3_ext/quant/exl3_gemm.cu:341-680."""
+    _need_cuda(A, B, C, suh, A_had, svh, indices, weights, size_n_list, c_ptrs)
+    _dtype(A, torch.half, "A")
+    _dtype(B, torch.long, "B"); _dtype(suh, torch.long, "suh"); _dtype(svh, torch.long, "svh")
+    c_fp32 = C.dtype == torch.float
+    if not c_fp32:
+        _dtype(C, torch.half, "C")
+    if A.dim() != 3 or C.dim() != 3 or B.dim() != 1 or suh.dim() != 1 or svh.dim() != 1:
+        raise RuntimeError("exl3_mgemm: incorrect number of dimensions")
+    if A.shape[1] != C.shape[1]:
+        raise RuntimeError("A and C incompatible shapes")
+    if B.shape[0] != suh.shape[0] or B.shape[0] != svh.shape[0]:
+        raise RuntimeError("B, suh and svh tables must have the same length")
+    bszm_in, m, k = A.shape
+    bszm_out, _, n = C.shape
+    num_c_ptrs = 0
+    if size_n_list is not None:
+        if c_ptrs is None:
+            raise RuntimeError("exl3_mgemm: size_n_list requires c_ptrs")
+        _dtype(size_n_list, torch.int, "size_n_list"); _dtype(c_ptrs, torch.long, "c_ptrs")
+        num_c_ptrs = c_ptrs.shape[0]
+    bszm = max(bszm_in, num_c_ptrs if size_n_list is not None else bszm_out)
+    if A_had.numel() < bszm * m * k:
+        raise RuntimeError("exl3_mgemm: A_had must hold bszm * m * k elements")
+    num_indices = 0
+    if indices is not None:
+        if indices.dim() != 2:
+            raise RuntimeError("indices: incorrect number of dimensions, must be 2")
+        _dtype(indices, torch.long, "indices")
+        num_indices = indices.shape[1]
+    if weights is not None:
+        if weights.dim() != 2:
+            raise RuntimeError("weights: incorrect number of dimensions, must be 2")
+        _dtype(weights, torch.half, "weights")
+    with torch.cuda.device(A.device):
+        return _check(_lib.exl3b_mgemm(
+            _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had), _ptr(svh),
+            _ptr(indices), num_indices, _ptr(weights),
+            bszm_in, bszm_out, m, k, n, int(K), _cb(mcg, mul1), int(c_fp32),
+            int(min_index), int(max_index), int(num_tokens),
+            _ptr(size_n_list), _ptr(c_ptrs), num_c_ptrs, int(force_shape_idx), int(force_num_sms)))
+
+
+def reconstruct_slice(unpacked, packed, K: int, mcg, mul1, n_offset: int) -> None:
+    """exllamav3_ext/quant/reconstruct.cu:98-144."""
+    _need_cuda(unpacked, packed)
+    if unpacked.shape[0] != packed.shape[0] * 16:
+        raise RuntimeError("unpacked and packed incompatible shapes")
+    if packed.shape[2] != 256 * K // 16:
+        raise RuntimeError("packed: incorrect size in dimension 2")
+    _dtype(unpacked, torch.half, "unpacked")
+    assert unpacked.is_contiguous() and packed.is_contiguous()
+    with torch.cuda.device(unpacked.device):
+        _check(_lib.exl3b_reconstruct(_stream(unpacked), _ptr(unpacked), _ptr(packed), unpacked.shape[0],
+                                      unpacked.shape[1], packed.shape[1], int(K), _cb(mcg, mul1), int(n_offset)))
+
+
+def reconstruct(unpacked, packed, K: int, mcg, mul1) -> None:
+    """exllamav3_ext/quant/reconstruct.cu:375-386."""
+    if unpacked.shape[1] != packed.shape[1] * 16:
+        raise RuntimeError("unpacked and packed incompatible shapes")
+    reconstruct_slice(unpacked, packed, K, mcg, mul1, 0)
+
+
+def reconstruct_had_slice(unpacked, packed, suh, svh, K: int, mcg, mul1, n_offset: int) -> None:
+    """exllamav3_ext/quant/reconstruct.cu:324-373."""
+    _need_cuda(unpacked, packed, suh, svh)
+    if unpacked.shape[0] != packed.shape[0] * 16:
+        raise RuntimeError("unpacked and packed incompatible shapes")
+    if packed.shape[2] != 256 * K // 16:
+        raise RuntimeError("packed: incorrect size in dimension 2")
+    _dtype(unpacked, torch.half, "unpacked"); _dtype(suh, torch.half, "suh"); _dtype(svh, torch.half, "svh")
+    if suh.numel() < unpacked.shape[0]:
+        raise RuntimeError("reconstruct_had: suh size")
+    if svh.numel() < unpacked.shape[1]:
+        raise RuntimeError("reconstruct_had: svh size")
+    assert unpacked.is_contiguous() and packed.is_contiguous()
+    with torch.cuda.device(unpacked.device):
+        _check(_lib.exl3b_reconstruct_had(_stream(unpacked), _ptr(unpacked), _ptr(packed), _ptr(suh), _ptr(svh),
+                                          unpacked.shape[0], unpacked.shape[1], packed.shape[1], int(K),
+                                          _cb(mcg, mul1), int(n_offset)))
+
+
+def had_r_128(input, output, pre_scale, post_scale, scale: float) -> None:
+    """exllamav3_ext/quant/hadamard.cu:88-173."""
+    _need_cuda(input, output, pre_scale, post_scale)
+    if input.shape != output.shape:
+        raise RuntimeError("input and output incompatible shapes")
+    if input.dim() != 2:
+        raise RuntimeError("input: incorrect number of dimensions, must be 2")
+    if input.dtype == torch.half:
+        _dtype(output, torch.half, "output"); fp32 = 0
+    elif input.dtype == torch.float:
+        _dtype(output, torch.float, "output"); fp32 = 1
+    else:
+        raise RuntimeError("unsupported datatype")
+    assert input.is_contiguous() and output.is_contiguous()
+    with torch.cuda.device(input.device):
+        _check(_lib.exl3b_had_r_128(_stream(input), _ptr(input), _ptr(output), _ptr(pre_scale), _ptr(post_scale),
+                                    float(scale), input.shape[0], input.shape[1], fp32))
+
+
+def hgemm(a, b, c) -> None:
+    """Row-major fp16 a @ b -> c (fp16 or fp32), fp32 accumulate.  exllamav3_ext/hgemm.cu:19-102."""
+    _need_cuda(a, b, c)
+    if c.dtype not in (torch.half, torch.float):
+        raise RuntimeError("c must be float32 or float16")
+    _dtype(a, torch.half, "a"); _dtype(b, torch.half, "b")
+    if b.dim() != 2 or c.dim() < 2:
+        raise RuntimeError("hgemm: incorrect number of dimensions")
+    k = a.shape[-1]
+    m = a.numel() // k if k else 0
+    n = b.shape[-1]
+    if k != b.shape[0] or c.shape[-1] != n:
+        raise RuntimeError("a, b and c incompatible shapes")
+    if c.stride(-1) != 1:
+        raise RuntimeError("c must have contiguous columns")
+    assert a.is_contiguous() and b.is_contiguous()
+    with torch.cuda.device(a.device):
+        _check(_lib.exl3b_hgemm(_stream(a), _ptr(a), _ptr(b), _ptr(c), m, k, n, int(c.dtype == torch.float),
+                                c.stride(-2)))
+
+
+def g_get_cc(device: int) -> int:
+    return _check(_lib.exl3b_cc(int(device)))
+
+
+def g_get_num_sms(device: int) -> int:
+    return _check(_lib.exl3b_num_sms(int(device)))
+
+
+def exl3_gemm_num_kernel_shapes() -> int:
+    """The reference enumerates 4 mma.sync tile shapes (exl3_kernel_map.cuh:53-60); here: SIMT and tcgen05 paths."""
+    return 2
+
+
+def exl3_gemm_shape_compat(shape_idx: int, size_m: int, size_k: int, size_n: int, K: int) -> bool:
+    return size_k % 128 == 0 and size_n % 128 == 0 and 1 <= K <= 8 and shape_idx in (1, 2)
+
+
+class BC_LinearEXL3:
+    """
+    Holder of one quantized linear's tensors with run / run_alloc, as exllamav3_ext/libtorch/linear_bc.h:13-35 and
+    linear.cpp:34-71.  `xh` is the caller's shared (1, k) scratch used for single-row inputs.
+    """
+
+    def __init__(self, trellis, suh, svh, K: int, bias, mcg: bool, mul1: bool, xh):
+        self.trellis, self.suh, self.svh, self.K = trellis, suh, svh, int(K)
+        self.bias, self.mcg, self.mul1, self.xh = bias, bool(mcg), bool(mul1), xh
+
+    def run(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        if x.numel() == x.shape[-1] and self.xh is not None:
+            exl3_gemm(x, self.trellis, y, self.suh, self.xh, self.svh, -1, self.mcg, self.mul1, 0)
+        else:
+            xh_ = torch.empty_like(x)
+            exl3_gemm(x, self.trellis, y, self.suh, xh_, self.svh, -1, self.mcg, self.mul1, 0)
+        if self.bias is not None:
+            y += self.bias
+
+    def run_alloc(self, x: torch.Tensor, out_features: int, output_fp32: bool) -> torch.Tensor:
+        out_shape = list(x.shape)
+        out_shape[-1] = out_features
+        y = torch.empty(out_shape, dtype=torch.float if output_fp32 else torch.half, device=x.device)
+        if out_features == 0:
+            return y
+        self.run(x.view(-1, x.shape[-1]), y.view(-1, out_features))
+        return y

@@ -1,0 +1,161 @@
+/*
+ * exl3b200 -- Blackwell-native (sm_100a) EXL3 quantized-GEMM path, C ABI.
+ *
+ * Drop-in boundary for the hot path of turboderp-org/exllamav3 (reference paths are relative to
+ * /root/reference/exllamav3/).  Every entry point replaces one pybind11 binding of the reference's
+ * `exllamav3_ext` module; the reference-side shim a maintainer would add is shown in INTEGRATION.md and is
+ * implemented in exllamav3_b200/ext.py (ctypes).
+ *
+ * Conventions
+ *   - plain pointers and sizes only: no torch / ATen types cross this boundary.
+ *   - every `const void*` / `void*` tensor argument is a DEVICE pointer on the current CUDA device unless the
+ *     name ends in `_host`.  `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - the caller owns all buffers.  The library lazily allocates per-device scratch (split-K partials,
+ *     tile counters) with cudaMalloc on first use, like the reference's DevCtx (exllamav3_ext/quant/exl3_devctx.cu:24-70).
+ *   - return value: >= 0 on success (exl3b_gemm / exl3b_mgemm return a kernel-path tag like the reference's
+ *     exl3_gemm, exllamav3_ext/quant/exl3_gemm.cu:234,247,308), < 0 = -(enum exl3b_status).  On error nothing was launched
+ *     and exl3b_last_error() describes the problem (the reference raises via TORCH_CHECK, exllamav3_ext/util.h:24-37;
+ *     exllamav3_b200/ext.py turns negative codes into RuntimeError with the same wording family).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns -EXL3B_ERR_CUDA.
+ *   - cb (codebook): 0 = 3INST (default), 1 = MCG, 2 = MUL1   (exllamav3_ext/quant/exl3_gemm.cu:173-176).
+ *   - trellis layout: (k/16, n/16, 16*K) uint16, exactly the on-disk / reference layout (exllamav3_ext/quant/exl3_gemm.cu:27).
+ */
+#ifndef EXL3B200_H
+#define EXL3B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXL3B_ABI_VERSION 1
+
+enum exl3b_status
+{
+    EXL3B_OK = 0,
+    EXL3B_ERR_SHAPE = 1,      /* dimension / divisibility violation                      */
+    EXL3B_ERR_ARG = 2,        /* null pointer, bad K / cb / flag                         */
+    EXL3B_ERR_CUDA = 3,       /* CUDA runtime error (message has cudaGetErrorString)     */
+    EXL3B_ERR_UNSUPPORTED = 4 /* valid in the reference but not implemented here         */
+};
+
+/* Kernel-path tags returned by exl3b_gemm / exl3b_mgemm */
+#define EXL3B_TAG_NOP 0        /* empty problem                                            */
+#define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
+#define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM                               */
+
+int exl3b_abi_version(void);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* exl3b_last_error(void);
+
+/* Device introspection -- replaces ext.g_get_num_sms / ext.g_get_cc (exllamav3_ext/bindings.cpp:130-131).
+   Return the value, or a negative status. */
+int exl3b_num_sms(int device);
+int exl3b_cc(int device);
+
+/* Force a kernel path for exl3b_gemm on this process: 0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC.
+   (The reference exposes force_shape_idx / force_num_sms per call for the same purpose.) Returns previous value. */
+int exl3b_set_gemm_path(int tag);
+
+/*
+ * exl3b_gemm -- replaces ext.exl3_gemm (exllamav3_ext/bindings.cpp:126, exllamav3_ext/quant/exl3_gemm.cuh:21-33,
+ * implementation exllamav3_ext/quant/exl3_gemm.cu:110-309).
+ *
+ *   C[m,n] = had128( had128(A[m,k] * suh) @ W_hat[k,n] ) * svh
+ *
+ *   A      (m, k) fp16, contiguous rows
+ *   B      trellis (k/16, n/16, 16*K) uint16
+ *   C      (m, n) fp16 (c_fp32 = 0) or fp32 (c_fp32 = 1); overwritten, need not be zeroed
+ *   suh    (k) fp16 or NULL (NULL: A is already in the rotated basis, no input transform)
+ *   A_had  (m, k) fp16 scratch for the transformed input; may alias A; may be NULL (library scratch is used)
+ *   svh    (n) fp16 or NULL (NULL: no output transform)
+ *   k % 128 == 0, n % 128 == 0, 1 <= K <= 8.
+ *   force_shape_idx, force_num_sms: accepted for signature parity (exl3_gemm.cuh:28,32); > 0 values are honoured
+ *   only where they have a meaning here (force_num_sms caps the persistent grid).
+ */
+int exl3b_gemm(void* stream,
+               const void* A, const void* B, void* C,
+               const void* suh, void* A_had, const void* svh,
+               int m, int k, int n, int K, int cb, int c_fp32,
+               int force_shape_idx, int force_num_sms);
+
+/*
+ * exl3b_mgemm -- replaces ext.exl3_mgemm (exllamav3_ext/bindings.cpp:146, exllamav3_ext/quant/exl3_gemm.cuh:58-78; semantics
+ * exllamav3_ext/quant/exl3_gemm.cu:341-381).
+ *
+ *   A         (bszm_in, m, k) fp16
+ *   B_ptrs, suh_ptrs, svh_ptrs : device arrays of device addresses, one per quantized matrix
+ *   C         (bszm_out, m, n) fp16|fp32
+ *   A_had     fp16 scratch, at least max(bszm_in, bszm_out) * m * k elements (exl3_gemm.cu:452-453)
+ *   indices   device int64 [num_indices] or NULL; negative entries skip the slot
+ *   weights   device fp16 [num_indices] or NULL; if given every result is scaled and groups of
+ *             (slots / num_tokens) are summed into C[t]
+ *   min_index/max_index : expert-range filter with rebasing (min_index < 0 = off)
+ *   size_n_list (device int32, per matrix) + c_ptrs (device addresses, per matrix): per-matrix output widths
+ *             (NULL = uniform n, outputs in C); num_c_ptrs = number of entries.
+ */
+int exl3b_mgemm(void* stream,
+                const void* A, const uint64_t* B_ptrs, void* C,
+                const uint64_t* suh_ptrs, void* A_had, const uint64_t* svh_ptrs,
+                const int64_t* indices, int num_indices, const void* weights,
+                int bszm_in, int bszm_out, int m, int k, int n, int K, int cb, int c_fp32,
+                int min_index, int max_index, int num_tokens,
+                const int32_t* size_n_list, const uint64_t* c_ptrs, int num_c_ptrs,
+                int force_shape_idx, int force_num_sms);
+
+/*
+ * exl3b_reconstruct -- replaces ext.reconstruct / ext.reconstruct_slice (exllamav3_ext/bindings.cpp:122-123,
+ * exllamav3_ext/quant/reconstruct.cu:98-144,375-386):  trellis -> W_hat fp16, bit-exact.
+ *   unpacked (k, n_out) fp16 contiguous; packed (k/16, packed_tiles_n, 16*K) uint16; columns
+ *   [n_offset, n_offset + n_out) of the packed tensor are decoded.  n_out % 128 == 0, n_offset % 128 == 0.
+ */
+int exl3b_reconstruct(void* stream, void* unpacked, const void* packed,
+                      int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset);
+
+/*
+ * exl3b_reconstruct_had -- replaces ext.reconstruct_had_slice (exllamav3_ext/bindings.cpp:124, exllamav3_ext/quant/reconstruct.cu:324-373):
+ *   unpacked = diag(suh) . H128 . W_hat . H128 . diag(svh)  (original-basis weights), k % 128 == 0, n_out % 128 == 0;
+ *   svh is pre-offset by the caller (points at the first emitted column), suh has k entries.
+ */
+int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed,
+                          const void* suh, const void* svh,
+                          int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset);
+
+/*
+ * exl3b_had_r_128 -- replaces ext.had_r_128 (exllamav3_ext/bindings.cpp:125, exllamav3_ext/quant/hadamard.cu:88-173):
+ *   out = (in.view(-1,128) @ H128) * scale / sqrt(128), optional per-column fp16 pre_scale OR post_scale
+ *   (pre_scale wins if both given, as in the reference).  is_fp32 selects fp32 in/out, else fp16.  In place OK.
+ */
+int exl3b_had_r_128(void* stream, const void* in, void* out,
+                    const void* pre_scale, const void* post_scale, float scale,
+                    int rows, int cols, int is_fp32);
+
+/*
+ * exl3b_hgemm -- replaces ext.hgemm (exllamav3_ext/bindings.cpp:147, exllamav3_ext/hgemm.cu:19-102): row-major c = a @ b,
+ * a (m,k) fp16, b (k,n) fp16, c (m,n) fp16|fp32 with row stride c_stride (elements), fp32 accumulate.
+ */
+int exl3b_hgemm(void* stream, const void* a, const void* b, void* c,
+                int m, int k, int n, int c_fp32, int64_t c_stride);
+
+/*
+ * Host-buffer convenience used by the end-to-end benchmark leg and by non-torch integrations:
+ * copies A_host (pinned or pageable, m*k fp16) to the device, runs exl3b_gemm against device-resident weights,
+ * copies C back to C_host and synchronises the stream.  d_A / d_C / d_A_had are caller-provided device staging
+ * buffers of the same sizes.
+ */
+int exl3b_gemm_host(void* stream,
+                    const void* A_host, void* C_host,
+                    void* d_A, void* d_C, void* d_A_had,
+                    const void* B, const void* suh, const void* svh,
+                    int m, int k, int n, int K, int cb, int c_fp32);
+
+/* Count of kernels launched by this library in this process (for bench.py's gpu_launches claim). */
+int64_t exl3b_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXL3B200_H */

@@ -1,0 +1,88 @@
+"""
+C-ABI checks that need no GPU: libexl3b200.so loads, exports every symbol include/exl3b200.h declares, and its
+argument validation (the reference's TORCH_CHECKs) fires before any CUDA work.  No compute is attempted.
+"""
+import ctypes, os, re
+import numpy as np
+import pytest
+import torch
+from conftest import ROOT
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "exl3b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(exl3b_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from exllamav3_b200 import ext
+    syms = _declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(ext.lib, s), f"{s} declared in include/exl3b200.h but not exported"
+    assert ext.lib.exl3b_abi_version() == 1
+
+
+def test_validation_errors_without_gpu():
+    from exllamav3_b200 import ext
+    lib = ext.lib
+    one = ctypes.c_void_p(16)      # never dereferenced: validation fails first
+    # K out of range
+    assert lib.exl3b_gemm(None, one, one, one, one, one, one, 1, 128, 128, 9, 0, 0, -1, 0) == -2
+    assert b"K must be 1..8" in lib.exl3b_last_error()
+    # n not divisible by 128  (exl3_gemm.cu:37-39 "n % 128 == 0")
+    assert lib.exl3b_gemm(None, one, one, one, one, one, one, 1, 128, 64, 4, 0, 0, -1, 0) == -1
+    assert b"divisible by 128" in lib.exl3b_last_error()
+    # reconstruct: offsets (reconstruct.cu:117-120)
+    assert lib.exl3b_reconstruct(None, one, one, 16, 128, 8, 4, 0, 64) == -1
+    assert b"n_offset must be divisible by 128" in lib.exl3b_last_error()
+    assert lib.exl3b_reconstruct(None, one, one, 16, 256, 8, 4, 0, 0) == -1
+    assert b"exceeds packed tensor bounds" in lib.exl3b_last_error()
+    # had_r_128 (hadamard.cu:101)
+    assert lib.exl3b_had_r_128(None, one, one, None, None, 1.0, 1, 100, 0) == -1
+    # mgemm argument rules (exl3_gemm.cu:408-410,441-446)
+    r = lib.exl3b_mgemm(None, one, one, one, one, one, one, one, 2, None, 1, 2, 1, 128, 128, 4, 0, 0,
+                        0, 1, 2, None, None, 0, -1, 0)
+    assert r == -2 and b"num_tokens > 1" in lib.exl3b_last_error()
+    # empty problems are no-ops, not errors
+    assert lib.exl3b_gemm(None, None, None, None, None, None, None, 0, 128, 128, 4, 0, 0, -1, 0) == 0
+
+
+def test_python_surface_rejects_cpu_tensors_and_bad_dtypes():
+    from exllamav3_b200 import ext
+    a = torch.zeros(1, 128, dtype=torch.half)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ext.had_r_128(a, a, None, None, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ext.exl3_gemm(a, torch.zeros(8, 8, 64, dtype=torch.int16), torch.zeros(1, 128, dtype=torch.half),
+                      None, None, None, -1, False, True, 0)
+
+
+def test_reference_named_surface_is_complete():
+    # every binding of exllamav3_ext the qgemm path uses
+    from exllamav3_b200 import ext
+    for name in ["exl3_gemm", "exl3_mgemm", "reconstruct", "reconstruct_slice", "reconstruct_had_slice",
+                 "had_r_128", "hgemm", "BC_LinearEXL3", "g_get_cc", "g_get_num_sms",
+                 "exl3_gemm_num_kernel_shapes", "exl3_gemm_shape_compat"]:
+        assert hasattr(ext, name), name
+
+
+def test_linear_exl3_tp_slice_host_logic():
+    # slicing rules of LinearEXL3.tp_import_split (modules/quant/exl3.py:284-330) on CPU tensors: no kernels run
+    from exllamav3_b200 import LinearEXL3
+    from oracle import exl3_oracle as orc
+    k, n, K = 256, 384, 3
+    tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+    bias = torch.arange(n, dtype=torch.half)
+    lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh),
+                     trellis=torch.from_numpy(tr), mul1=torch.zeros((), dtype=torch.int), bias=bias)
+    col = lin.tp_slice((True, 128, 384))
+    assert col.in_features == k and col.out_features == 256
+    assert torch.equal(col.trellis, lin.trellis[:, 8:24, :]) and torch.equal(col.svh, lin.svh[128:384])
+    assert torch.equal(col.suh, lin.suh) and torch.equal(col.bias, bias[128:384]) and col.mul1 and not col.mcg
+    row0 = lin.tp_slice((False, 0, 128)); row1 = lin.tp_slice((False, 128, 256))
+    assert row0.in_features == 128 and row0.out_features == n
+    assert torch.equal(row1.trellis, lin.trellis[8:16]) and torch.equal(row1.suh, lin.suh[128:256])
+    assert row0.bias is not None and row1.bias is None            # bias only on the shard with first == 0
+    assert col.trellis.is_contiguous() and row1.trellis.is_contiguous()

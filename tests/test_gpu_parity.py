@@ -1,0 +1,303 @@
+"""
+GPU parity tests (B200): the CUDA path, called through the C ABI (exllamav3_b200.ext -> libexl3b200.so), against the
+CPU oracle on the same seeded inputs, against the committed golden outputs of the reference's own CUDA kernels, and
+-- at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (stated per north_star):
+  reconstruct, had_r_128 (fp16 and fp32)   : bit-exact
+  exl3_gemm / exl3_mgemm vs fp64 oracle    : max-abs <= 2e-3 * max|y| + 1 output ulp,  rel-RMS <= 1e-3
+  exl3_gemm vs reference exl3_gemm (golden): max-abs <= 4e-3 * max|y|,  rel-RMS <= 2e-3 (the reference carries fp16
+                                             split-K partial rounding, exl3_gemm_inner.cuh:501-503)
+  reconstruct_had vs fp64                  : max-abs <= 2e-3 * max|W|   (reference test: tests/test_reconstruct_had.py:56-58)
+  kernel path vs reconstruct+hgemm path    : rtol = atol = 0.05         (reference test: tests/test_qgemm.py:52-53)
+"""
+import os
+import numpy as np
+import pytest
+import torch
+from conftest import GOLDEN
+from oracle import exl3_oracle as orc
+from oracle import gen_golden_gpu as gg
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def rel_err(y, ref):
+    y = y.astype(np.float64); ref = ref.astype(np.float64)
+    err = np.abs(y - ref)
+    return err.max() / max(np.abs(ref).max(), 1e-30), np.sqrt((err ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-30)
+
+
+def run_gemm(ext, dev, x, tr, suh, svh, K, cb, fp32, a_had=True):
+    m, n = x.shape[0], tr.shape[1] * 16
+    A = T(x, dev)
+    C = torch.full((m, n), float("nan"), dtype=torch.float if fp32 else torch.half, device=dev)
+    A_had = torch.empty_like(A) if a_had else None
+    tag = ext.exl3_gemm(A, T(tr, dev), C, T(suh, dev), A_had, T(svh, dev), -1, cb == 1, cb == 2, 0)
+    torch.cuda.synchronize()
+    return C.cpu().numpy(), (A_had.cpu().numpy() if a_had else None), tag
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("K", range(1, 9))
+@pytest.mark.parametrize("cb", range(3))
+def test_reconstruct_bitexact(cuda, K, cb):
+    from exllamav3_b200 import ext
+    k, n = 64, 256
+    tr, _, _, _ = orc.make_synthetic(k, n, K)
+    w = torch.empty((k, n), dtype=torch.half, device=cuda)
+    ext.reconstruct(w, T(tr, cuda), K, cb == 1, cb == 2)
+    ref = orc.reconstruct(tr, K, cb)
+    assert (w.cpu().numpy().view(np.uint16) == ref.view(np.uint16)).all()
+
+
+def test_reconstruct_slice_and_edge_cases(cuda):
+    from exllamav3_b200 import ext
+    K, cb, k, n = 5, 1, 32, 512
+    tr, _, _, _ = orc.make_synthetic(k, n, K)
+    ref = orc.reconstruct(tr, K, cb)
+    for off, nout in ((0, 128), (128, 256), (384, 128)):
+        w = torch.empty((k, nout), dtype=torch.half, device=cuda)
+        ext.reconstruct_slice(w, T(tr, cuda), K, True, False, off)
+        assert (w.cpu().numpy().view(np.uint16) == ref[:, off:off + nout].view(np.uint16)).all()
+    # empty output is a no-op (reconstruct.cu:113-114)
+    ext.reconstruct_slice(torch.empty((k, 0), dtype=torch.half, device=cuda), T(tr, cuda), K, True, False, 0)
+    with pytest.raises(RuntimeError, match="divisible by 128"):
+        ext.reconstruct_slice(torch.empty((k, 64), dtype=torch.half, device=cuda), T(tr, cuda), K, True, False, 0)
+    with pytest.raises(RuntimeError, match="exceeds packed tensor bounds"):
+        ext.reconstruct_slice(torch.empty((k, 256), dtype=torch.half, device=cuda), T(tr, cuda), K, True, False, 384)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("mode", ["none", "pre", "post"])
+def test_had_r_128_bitexact(cuda, dt, mode):
+    from exllamav3_b200 import ext
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((37, 384)).astype(np.float16 if dt == "f16" else np.float32)
+    sc = (np.sign(rng.standard_normal(384)) * rng.uniform(0.5, 2, 384)).astype(np.float16)
+    for scale in (1.0, 0.37):
+        xi = T(x, cuda); yo = torch.empty_like(xi)
+        ext.had_r_128(xi, yo, T(sc, cuda) if mode == "pre" else None, T(sc, cuda) if mode == "post" else None, scale)
+        ref = orc.had_r_128(x, sc if mode == "pre" else None, sc if mode == "post" else None, scale)
+        got = yo.cpu().numpy()
+        view = np.uint16 if dt == "f16" else np.uint32
+        assert (got.view(view) == ref.view(view)).all()
+    # in place
+    xi = T(x, cuda)
+    ext.had_r_128(xi, xi, None, None, 1.0)
+    assert (xi.cpu().numpy().view(view) == orc.had_r_128(x).view(view)).all()
+
+
+@pytest.mark.parametrize("K,cb", [(1, 2), (2, 2), (3, 0), (4, 2), (4, 0), (4, 1), (5, 2), (6, 2), (7, 1), (8, 2)])
+@pytest.mark.parametrize("m", [1, 5, 16, 17])
+def test_gemm_vs_oracle(cuda, K, cb, m):
+    from exllamav3_b200 import ext
+    k, n = 512, 384
+    tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+    ref = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
+    for fp32 in (False, True):
+        y, xh, tag = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, fp32)
+        assert tag in (ext.EXL3B_TAG_SIMT, ext.EXL3B_TAG_TC)
+        assert not np.isnan(y.astype(np.float32)).any()
+        xh_ref = orc.had_r_128(x, pre_scale=suh)
+        assert (xh.view(np.uint16) == xh_ref.view(np.uint16)).all()          # input transform bit-exact
+        mx, rms = rel_err(y, ref)
+        ulp = 2.0 ** -10 if not fp32 else 0.0
+        assert mx <= 2e-3 + ulp, (K, cb, m, fp32, mx)
+        assert rms <= 1e-3, (K, cb, m, fp32, rms)
+
+
+def test_gemm_without_scratch_and_ragged_rows(cuda):
+    from exllamav3_b200 import ext
+    K, cb, k, n = 4, 2, 256, 256
+    for m in (1, 3, 31, 33, 144):          # rows up to the reconstruct threshold (modules/quant/exl3.py:10)
+        tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+        ref = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
+        y, _, _ = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, True, a_had=False)
+        mx, rms = rel_err(y, ref)
+        assert mx <= 2e-3 and rms <= 1e-3, (m, mx, rms)
+    # A_had aliasing A is allowed (science/qgemm_benchmark.py:85)
+    tr, suh, svh, x = orc.make_synthetic(k, n, K, m=4)
+    A = T(x, cuda); C = torch.empty((4, n), dtype=torch.half, device=cuda)
+    ext.exl3_gemm(A, T(tr, cuda), C, T(suh, cuda), A, T(svh, cuda), -1, False, True, 0)
+    mx, rms = rel_err(C.cpu().numpy(), orc.exl3_gemm_f64(x, tr, suh, svh, K, cb))
+    assert mx <= 3e-3 and rms <= 1e-3
+
+
+def test_gemm_vs_reference_cuda_golden(cuda):
+    p = os.path.join(GOLDEN, "ref_gpu.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden/ref_gpu.npz not generated yet")
+    from exllamav3_b200 import ext
+    g = np.load(p)
+    for (m, k, n, K, cb, fp32) in gg.gemm_cases():
+        tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+        key = f"gemm_{m}_{k}_{n}_{K}_{cb}_{int(fp32)}"
+        y, xh, _ = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, fp32)
+        assert (xh.view(np.uint16) == g[key + "_xh"].view(np.uint16)).all(), key
+        mx, rms = rel_err(y, g[key])
+        assert mx <= 4e-3 and rms <= 2e-3, (key, mx, rms)
+    for (K, cb, k, n) in gg.reconstruct_cases():
+        tr, _, _, _ = orc.make_synthetic(k, n, K)
+        w = torch.empty((k, n), dtype=torch.half, device=cuda)
+        ext.reconstruct(w, T(tr, cuda), K, cb == 1, cb == 2)
+        assert (w.cpu().numpy().view(np.uint16) == g[f"rec_{K}_{cb}_{k}_{n}"].view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("K,cb", [(3, 0), (4, 2), (2, 1), (6, 2)])
+def test_reconstruct_had(cuda, K, cb):
+    # tests/test_reconstruct_had.py:45-68: fused W vs explicit Sylvester, max|err|/max|ref| < 2e-3, incl. slice path
+    from exllamav3_b200 import ext
+    k, n = 256, 384
+    tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+    ref = orc.get_weight_tensor_f64(tr, suh, svh, K, cb)
+    w = torch.empty((k, n), dtype=torch.half, device=cuda)
+    ext.reconstruct_had_slice(w, T(tr, cuda), T(suh, cuda), T(svh, cuda), K, cb == 1, cb == 2, 0)
+    got = w.cpu().numpy().astype(np.float64)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-3
+    w2 = torch.empty((k, 256), dtype=torch.half, device=cuda)
+    ext.reconstruct_had_slice(w2, T(tr, cuda), T(suh, cuda), T(svh[128:], cuda), K, cb == 1, cb == 2, 128)
+    assert torch.equal(w2.cpu(), w[:, 128:].cpu())
+
+
+def test_hgemm(cuda):
+    from exllamav3_b200 import ext
+    rng = np.random.default_rng(0)
+    for (m, k, n) in ((1, 128, 128), (37, 256, 384), (300, 512, 256)):
+        a = rng.standard_normal((m, k)).astype(np.float16); b = rng.standard_normal((k, n)).astype(np.float16)
+        ref = a.astype(np.float64) @ b.astype(np.float64)
+        for dt in (torch.half, torch.float):
+            c = torch.empty((m, n), dtype=dt, device=cuda)
+            ext.hgemm(T(a, cuda), T(b, cuda), c)
+            mx, rms = rel_err(c.cpu().numpy(), ref)
+            assert mx <= (2e-3 if dt == torch.half else 1e-4), (m, k, n, dt, mx)
+    # strided C rows (hgemm.cu:52-54), as used by the sliced lm_head path (modules/quant/exl3.py:199-211)
+    a = rng.standard_normal((5, 128)).astype(np.float16); b = rng.standard_normal((128, 128)).astype(np.float16)
+    cfull = torch.zeros((5, 384), dtype=torch.half, device=cuda)
+    ext.hgemm(T(a, cuda), T(b, cuda), cfull[:, 128:256])
+    ref = (a.astype(np.float64) @ b.astype(np.float64))
+    assert rel_err(cfull[:, 128:256].cpu().numpy(), ref)[0] <= 2e-3 and float(cfull[:, :128].abs().max()) == 0.0
+
+
+def test_linear_exl3_kernel_vs_reconstruct_path(cuda):
+    # the reference's own pin of this path: tests/test_qgemm.py:31-53 (rtol = atol = 0.05), m list from there
+    from exllamav3_b200 import LinearEXL3
+    K, k, n = 3, 1024, 512
+    tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+    lin = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
+                     mul1=torch.zeros((), dtype=torch.int, device=cuda))
+    torch.manual_seed(0)
+    for m in (1, 2, 8, 16, 17, 31, 32, 33, 256, 2048):
+        x = torch.randn((1, m, k), dtype=torch.half, device=cuda)
+        a = lin.forward(x, {"reconstruct": False}) if m <= 144 else lin.forward(x, {})
+        b = lin.forward(x, {"reconstruct": True})
+        torch.testing.assert_close(a, b, rtol=0.05, atol=0.05)
+        assert a.shape == (1, m, n)
+        ref = orc.exl3_gemm_f64(x.view(m, k).cpu().numpy(), tr, suh, svh, K, 2)
+        mx, rms = rel_err(b.view(m, n).cpu().numpy(), ref)
+        assert mx <= 5e-3 and rms <= 2e-3, (m, mx, rms)
+    # fp32 output + bias
+    bias = torch.randn(n, dtype=torch.half, device=cuda)
+    lin2 = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
+                      mul1=torch.zeros((), dtype=torch.int, device=cuda), bias=bias, out_dtype=torch.float)
+    x = torch.randn((4, k), dtype=torch.half, device=cuda)
+    y = lin2.forward(x, {})
+    assert y.dtype == torch.float
+    torch.testing.assert_close(y, lin.forward(x, {}, torch.float) + bias, rtol=1e-3, atol=1e-3)
+    # get_weight_tensor == original-basis W
+    W = lin.get_weight_tensor().cpu().numpy().astype(np.float64)
+    Wref = orc.get_weight_tensor_f64(tr, suh, svh, K, 2)
+    assert np.abs(W - Wref).max() / np.abs(Wref).max() < 2e-3
+
+
+def test_mgemm_modes(cuda):
+    from exllamav3_b200 import ext, LinearEXL3, MultiLinear
+    k, n, K, m, mats, A, wts = gg.mgemm_inputs()
+    lins = [LinearEXL3(None, k, n, suh=T(t[1], cuda), svh=T(t[2], cuda), trellis=T(t[0], cuda),
+                       mul1=torch.zeros((), dtype=torch.int, device=cuda)) for t in mats]
+    ml = MultiLinear(cuda, lins)
+    trs = [t[0] for t in mats]; suhs = [t[1] for t in mats]; svhs = [t[2] for t in mats]
+    golden = np.load(os.path.join(GOLDEN, "ref_gpu.npz")) if os.path.exists(os.path.join(GOLDEN, "ref_gpu.npz")) else None
+    for fp32 in (False, True):
+        dt = torch.float if fp32 else torch.half
+        npdt = np.float32 if fp32 else np.float16
+        Ah = torch.empty((4, m, k), dtype=torch.half, device=cuda)
+        tol = 3e-3
+        # (a) one input, four outputs
+        C = torch.zeros((4, m, n), dtype=dt, device=cuda)
+        ext.exl3_mgemm(T(A[:1], cuda), ml.ptrs_trellis, C, ml.ptrs_suh, Ah, ml.ptrs_svh, None, None, K, -1,
+                       ml.mcg, ml.mul1, -1, -1, 0)
+        ref = orc.exl3_mgemm(A[:1], trs, suhs, svhs, K, 2, npdt, bszm_out=4)
+        assert rel_err(C.cpu().numpy(), ref)[0] <= tol
+        if golden is not None:
+            assert rel_err(C.cpu().numpy(), golden[f"mgemm_a_{int(fp32)}"])[0] <= 5e-3
+        # (b) indices with a skipped slot
+        C = torch.zeros((4, m, n), dtype=dt, device=cuda)
+        idx = torch.tensor([[2, -1, 0, 3]], dtype=torch.long, device=cuda)
+        ext.exl3_mgemm(T(A, cuda), ml.ptrs_trellis, C, ml.ptrs_suh, Ah, ml.ptrs_svh, idx, None, K, -1,
+                       ml.mcg, ml.mul1, -1, -1, 0)
+        ref = orc.exl3_mgemm(A, trs, suhs, svhs, K, 2, npdt, indices=[2, -1, 0, 3], bszm_out=4)
+        assert rel_err(C.cpu().numpy(), ref)[0] <= tol and float(C[1].abs().max()) == 0.0
+        if golden is not None:
+            assert rel_err(C.cpu().numpy(), golden[f"mgemm_b_{int(fp32)}"])[0] <= 5e-3
+        # (c) weighted reduction into C[0]
+        C = torch.zeros((4, m, n), dtype=dt, device=cuda)
+        idx = torch.tensor([[3, 1, 0, 2]], dtype=torch.long, device=cuda)
+        ext.exl3_mgemm(T(A[:1], cuda), ml.ptrs_trellis, C, ml.ptrs_suh, Ah, ml.ptrs_svh, idx,
+                       T(wts, cuda).view(1, 4), K, -1, ml.mcg, ml.mul1, -1, -1, 0)
+        ref = orc.exl3_mgemm(A[:1], trs, suhs, svhs, K, 2, npdt, indices=[3, 1, 0, 2], weights=wts, bszm_out=4)
+        assert rel_err(C[0].cpu().numpy(), ref[0])[0] <= tol
+        if golden is not None:
+            assert rel_err(C[0].cpu().numpy(), golden[f"mgemm_c_{int(fp32)}"])[0] <= 5e-3
+        # (d) expert-range filter [1, 3) with local tables
+        C = torch.zeros((4, m, n), dtype=dt, device=cuda)
+        ext.exl3_mgemm(T(A[:1], cuda), ml.ptrs_trellis[1:3].contiguous(), C, ml.ptrs_suh[1:3].contiguous(), Ah,
+                       ml.ptrs_svh[1:3].contiguous(), idx, T(wts, cuda).view(1, 4), K, -1, ml.mcg, ml.mul1, 1, 3, 0)
+        ref = orc.exl3_mgemm(A[:1], trs[1:3], suhs[1:3], svhs[1:3], K, 2, npdt, indices=[3, 1, 0, 2], weights=wts,
+                             min_index=1, max_index=3, bszm_out=4)
+        assert rel_err(C[0].cpu().numpy(), ref[0])[0] <= tol
+        if golden is not None:
+            assert rel_err(C[0].cpu().numpy(), golden[f"mgemm_d_{int(fp32)}"])[0] <= 5e-3
+
+
+def test_full_size_properties(cuda):
+    """
+    BASELINE.json sizes (Llama-3.1-8B shapes, K=4, mul1) where the numpy oracle is too slow for a dense check:
+      * linearity in x:  f(a x1 + b x2) ~= a f(x1) + b f(x2)
+      * column-split == slice of the full result; row-split partial sums == full result  (TP shard identity, 8e)
+      * spot check of 256 random output columns against the fp64 oracle restricted to those columns' 128-blocks
+    """
+    from exllamav3_b200 import ext, LinearEXL3
+    K, cb = 4, 2
+    for (k, n) in ((4096, 4096), (4096, 14336), (14336, 4096)):
+        tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+        lin = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
+                         mul1=torch.zeros((), dtype=torch.int, device=cuda), out_dtype=torch.float)
+        torch.manual_seed(k + n)
+        x1 = torch.randn((1, k), dtype=torch.half, device=cuda); x2 = torch.randn((1, k), dtype=torch.half, device=cuda)
+        y1, y2 = lin.forward(x1, {}), lin.forward(x2, {})
+        xs = (0.5 * x1.float() + 0.25 * x2.float()).half()
+        ys = lin.forward(xs, {})
+        lin_err = (ys - (0.5 * y1 + 0.25 * y2)).abs().max() / ys.abs().max()
+        assert float(lin_err) < 5e-3, (k, n, float(lin_err))
+        # TP identities
+        half_n = (n // 256) * 128
+        ca = lin.tp_slice((True, 0, half_n)); cb_ = lin.tp_slice((True, half_n, n))
+        ycat = torch.cat((ca.forward(x1, {}), cb_.forward(x1, {})), dim=-1)
+        assert float((ycat - y1).abs().max() / y1.abs().max()) < 1e-3
+        half_k = (k // 256) * 128
+        ra = lin.tp_slice((False, 0, half_k)); rb = lin.tp_slice((False, half_k, k))
+        ysum = ra.forward(x1[:, :half_k].contiguous(), {}) + rb.forward(x1[:, half_k:].contiguous(), {})
+        assert float((ysum - y1).abs().max() / y1.abs().max()) < 2e-3
+        # spot check: two random 128-column blocks against the oracle
+        rng = np.random.default_rng(n)
+        for blk in rng.choice(n // 128, 2, replace=False):
+            sl = slice(blk * 128, blk * 128 + 128)
+            ref = orc.exl3_gemm_f64(x1.cpu().numpy(), tr[:, blk * 8: blk * 8 + 8, :], suh, svh[sl], K, cb)
+            mx, rms = rel_err(y1[:, sl].cpu().numpy(), ref)
+            assert mx <= 2e-3 and rms <= 1e-3, (k, n, blk, mx, rms)
