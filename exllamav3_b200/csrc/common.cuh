@@ -113,10 +113,16 @@ int launch_hgemm(cudaStream_t stream, const half* a, const half* b, void* c, int
 // 128-point Sylvester Hadamard across one warp, 4 consecutive elements per lane, fp32.  Performs exactly the
 // additions of the reference's had_*_r_128_inner (hadamard_inner.cuh:118-131, 14-41): in-lane 4-point, then
 // xor-shuffle stages 1..16 with new = (lane & i ? -own : own) + partner.
+__device__ __forceinline__ void had128_warp_tail(float& h0, float& h1, float& h2, float& h3, int lane);
 __device__ __forceinline__ void had128_warp(float& h0, float& h1, float& h2, float& h3, int lane)
 {
     float s0 = h0 + h1, d0 = h0 - h1, s1 = h2 + h3, d1 = h2 - h3;
     h0 = s0 + s1; h1 = d0 + d1; h2 = s0 - s1; h3 = d0 - d1;
+    had128_warp_tail(h0, h1, h2, h3, lane);
+}
+// the five cross-lane stages (the in-lane 4-point stage already applied)
+__device__ __forceinline__ void had128_warp_tail(float& h0, float& h1, float& h2, float& h3, int lane)
+{
     #pragma unroll
     for (int i = 1; i < 32; i <<= 1)
     {

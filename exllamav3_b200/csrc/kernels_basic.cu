@@ -33,11 +33,22 @@ had_r_128_kernel(const void* __restrict__ in, void* __restrict__ out, const half
     }
 
     float v0, v1, v2, v3;
+    bool pre_done = false;
     if constexpr (FP32)
     {
         float4 v = *reinterpret_cast<const float4*>((const float*) in + off);
         v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
-        if constexpr (SCALE_MODE == 1) { v0 *= sc0; v1 *= sc1; v2 *= sc2; v3 *= sc3; }
+        if constexpr (SCALE_MODE == 1)
+        {
+            // Explicitly the contraction the reference binary performs for this (cold) variant, so results are
+            // bit-identical to it and independent of compiler mood: t = x1*a1; s = fma(x0,a0,t); d = fma(x0,a0,-t).
+            float t1 = __fmul_rn(v1, sc1), t3 = __fmul_rn(v3, sc3);
+            float s0 = __fmaf_rn(v0, sc0, t1), d0 = __fmaf_rn(v0, sc0, -t1);
+            float s1 = __fmaf_rn(v2, sc2, t3), d1 = __fmaf_rn(v2, sc2, -t3);
+            v0 = __fadd_rn(s0, s1); v1 = __fadd_rn(d0, d1); v2 = __fsub_rn(s0, s1); v3 = __fsub_rn(d0, d1);
+            had128_warp_tail(v0, v1, v2, v3, lane);
+            pre_done = true;
+        }
     }
     else
     {
@@ -51,7 +62,7 @@ had_r_128_kernel(const void* __restrict__ in, void* __restrict__ out, const half
         v0 = __low2float(a); v1 = __high2float(a); v2 = __low2float(b); v3 = __high2float(b);
     }
 
-    had128_warp(v0, v1, v2, v3, lane);
+    if (!pre_done) had128_warp(v0, v1, v2, v3, lane);
     v0 *= r_scale; v1 *= r_scale; v2 *= r_scale; v3 *= r_scale;
 
     if constexpr (FP32)
