@@ -73,6 +73,18 @@ int ensure_xh_scratch(DevCtx* ctx, size_t elems)
     return 0;
 }
 
+int ensure_xh_tiled(DevCtx* ctx, size_t bytes_per_slot)
+{
+    if (ctx->xh_tiled_slot_bytes >= bytes_per_slot) return 0;
+    EXL3B_CUDA(cudaDeviceSynchronize());
+    if (ctx->xh_tiled) cudaFree(ctx->xh_tiled);
+    size_t want = bytes_per_slot < (4u << 20) ? (4u << 20) : (bytes_per_slot + 1023) / 1024 * 1024;
+    EXL3B_CUDA(cudaMalloc(&ctx->xh_tiled, want * DevCtx::XH_SLOTS));
+    EXL3B_CUDA(cudaMemset(ctx->xh_tiled, 0, want * DevCtx::XH_SLOTS));
+    ctx->xh_tiled_slot_bytes = want;
+    return 0;
+}
+
 }  // namespace exl3b
 
 using namespace exl3b;
@@ -167,21 +179,8 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
     EXL3B_CHECK(A && B && C, EXL3B_ERR_ARG, "exl3_gemm: null tensor");
     DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
 
-    const half* xh = (const half*) A;
-    if (suh && k > 0)
-    {
-        half* dst = (half*) A_had;
-        if (!dst)
-        {
-            r = ensure_xh_scratch(ctx, (size_t) m * k); if (r) return r;
-            dst = ctx->xh_scratch;
-        }
-        r = launch_had_r_128(stream, A, dst, (const half*) suh, nullptr, 1.0f, m, k, false); if (r) return r;
-        xh = dst;
-    }
-
     GemmArgs g{};
-    g.xh = xh; g.B = (const uint32_t*) B; g.C = C; g.svh = (const half*) svh;
+    g.A = (const half*) A; g.suh = (const half*) suh; g.A_had = (half*) A_had; g.B = (const uint32_t*) B; g.C = C; g.svh = (const half*) svh;
     g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f;
     g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
 

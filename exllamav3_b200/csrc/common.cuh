@@ -35,7 +35,7 @@ struct MSlotTable
 struct DevCtx
 {
     static constexpr int NUM_SLOTS = 8;
-    static constexpr size_t WS_BYTES_PER_SLOT = 8u << 20;     // fp32 partials
+    static constexpr size_t WS_BYTES_PER_SLOT = 40u << 20;    // fp32 split-K partials (2 x 148 CTAs x 256 rows x 128 cols)
     static constexpr int COUNTERS_PER_SLOT = 32768;
     int device = -1;
     int num_sms = 0;
@@ -43,6 +43,9 @@ struct DevCtx
     float* ws = nullptr;          // NUM_SLOTS * WS_BYTES_PER_SLOT
     int* counters = nullptr;      // NUM_SLOTS * COUNTERS_PER_SLOT, zero-initialised once
     MSlotTable* tabs = nullptr;   // NUM_SLOTS mgemm slot tables
+    static constexpr int XH_SLOTS = 4;
+    uint8_t* xh_tiled = nullptr;  // XH_SLOTS tiled activation buffers for the tcgen05 path
+    size_t xh_tiled_slot_bytes = 0;
     half* xh_scratch = nullptr;   // input-transform scratch when the caller passes A_had = NULL
     size_t xh_scratch_elems = 0;
     uint64_t launch_seq = 0;
@@ -53,6 +56,7 @@ struct DevCtx
 };
 int get_ctx(DevCtx** out);       // context of the current device (lazy init), status code
 int ensure_xh_scratch(DevCtx* ctx, size_t elems);
+int ensure_xh_tiled(DevCtx* ctx, size_t bytes_per_slot);
 
 // ---- launchers implemented in the .cu files ------------------------------------------------------------------
 int launch_had_r_128(cudaStream_t stream, const void* in, void* out, const half* pre, const half* post,
@@ -64,7 +68,9 @@ int launch_reconstruct_had(cudaStream_t stream, half* unpacked, const uint16_t* 
 
 struct GemmArgs
 {
-    const half* xh;          // transformed input (m, k) [or raw A when no input transform]
+    const half* A;           // raw input (m, k)
+    const half* suh;         // may be null: no input transform
+    half* A_had;             // caller scratch for the transformed input (may be null / alias A)
     const uint32_t* B;
     void* C;
     const half* svh;         // may be null

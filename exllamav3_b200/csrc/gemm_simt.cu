@@ -173,8 +173,20 @@ static int pick_splits(DevCtx* ctx, int k, int n, int slots)
 int launch_gemm_simt(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 {
     int slot = ctx->next_slot();
+    const half* xh = a.A;
+    if (a.suh)
+    {
+        half* dst = a.A_had;
+        if (!dst)
+        {
+            int r = ensure_xh_scratch(ctx, (size_t) a.m * a.k); if (r) return r;
+            dst = ctx->xh_scratch;
+        }
+        int r = launch_had_r_128(stream, a.A, dst, a.suh, nullptr, 1.0f, a.m, a.k, false); if (r) return r;
+        xh = dst;
+    }
     SimtParams p{};
-    p.xh = a.xh; p.B = a.B; p.C = a.C; p.svh = a.svh; p.k = a.k; p.n = a.n; p.c_fp32 = a.c_fp32;
+    p.xh = xh; p.B = a.B; p.C = a.C; p.svh = a.svh; p.k = a.k; p.n = a.n; p.c_fp32 = a.c_fp32;
     p.m_total = a.m; p.out_scale = a.out_scale;
     p.splits = pick_splits(ctx, a.k, a.n, 1);
     p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);

@@ -1,8 +1,515 @@
-// placeholder until the tcgen05 path lands
+// tcgen05 / TMEM EXL3 decode-GEMM for sm_100a ("TC path", tag 200).
+//
+//   C[m, n] = had128( xh[m, k] @ W_hat[k, n] ) * svh,      xh = fp16( had128(A * suh) / sqrt(128) )
+//
+// Design (see DESIGN.md for the roofline arithmetic):
+//   * swap-AB: the decoded weights are the M = 128 operand of tcgen05.mma (one 128-column strip of W_hat^T), the
+//     activations are the N = 16..256 operand, so the weight stream is decoded exactly ONCE for any m <= 256
+//     (the reference re-streams and re-decodes B per 16-row slab, exl3_gemm_kernel.cuh:37-50).
+//   * persistent stream-K over work units of 128(k) x 128(n) weights: CTA c owns units [U*c/G, U*(c+1)/G), k fastest.
+//   * warp-specialised, 512 threads:
+//        warp 0      producer: cp.async.bulk (TMA engine) of the raw trellis rows + the activation tile into an
+//                    mbarrier ring (weights prefetch starts BEFORE griddepcontrol.wait: PDL overlap with the
+//                    previous kernel's tail)
+//        warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::f16 with A read from TMEM and B from
+//                    shared memory, accumulators in TMEM; also owns TMEM alloc/dealloc
+//        warps 4-11  decode: LDS the packed chunk, decode 16 weights per thread per 16x16 tile, tcgen05.st them
+//                    straight into the TMEM A-operand stage (decoded weights never touch shared memory)
+//        warps 12-15 epilogue: tcgen05.ld the accumulators, split-K combine through a global workspace
+//                    (last-arriver reduces in fixed order => deterministic), output Hadamard + svh, store
+//   * activations arrive pre-tiled in the no-swizzle K-major core-matrix layout tcgen05 wants, written by the
+//     input-transform kernel (fused suh scale + 128-point Hadamard), so the B tile is one contiguous bulk copy.
+//
+// Reference behaviour being replaced: exllamav3_ext/quant/exl3_gemm_kernel.cuh:8-50, exl3_gemm_inner.cuh:22-733.
 #include "common.cuh"
+#include "decode.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
 namespace exl3b {
-bool gemm_tc_supported(const GemmArgs&) { return false; }
-int launch_gemm_tc(cudaStream_t, DevCtx*, const GemmArgs&) { return fail(EXL3B_ERR_UNSUPPORTED, "tcgen05 path not built"); }
-bool hgemm_tc_supported(int, int, int, int64_t) { return false; }
-int launch_hgemm_tc(cudaStream_t, const half*, const half*, void*, int, int, int, bool, int64_t) { return fail(EXL3B_ERR_UNSUPPORTED, "tcgen05 hgemm not built"); }
+
+using namespace ptx;
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_DEC_WARP0 = 4;
+constexpr int TC_DEC_WARPS = 8;
+constexpr int TC_EPI_WARP0 = 12;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_A_STAGE_COLS = 64;          // 128 k-values x fp16, 2 per 32-bit TMEM column
+
+struct TcParams
+{
+    const uint8_t* xh_tiled;     // [k/128][NT/8][16][8][8] fp16 (core-matrix tiles)
+    const uint32_t* B;
+    void* C;
+    const half* svh;
+    int m, k, n, NT;
+    int c_fp32;
+    float out_scale;
+    float* ws;
+    int* counters;
+    int stages;                  // smem ring depth
+    int b_load_bytes;            // bytes of the activation tile copied per unit
+    int a_stages;                // TMEM A-operand stages (3 or 4)
+    int d_bufs;                  // TMEM accumulator buffers (1 or 2)
+    int tmem_cols;               // 256 or 512
+};
+
+struct TcSmemLayout
+{
+    int w_bytes, b_bytes, off_b, off_tile, off_bars, total;
+};
+
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int K, int NT, int stages)
+{
+    TcSmemLayout L;
+    L.w_bytes = 2048 * K;
+    L.b_bytes = NT * 256;
+    L.off_b = stages * L.w_bytes;
+    L.off_tile = L.off_b + stages * L.b_bytes;
+    L.off_bars = L.off_tile + 16 * 128 * 4;
+    L.total = L.off_bars + 512;
+    return L;
 }
+
+// ---- input transform into the tiled activation layout ---------------------------------------------------------
+template <bool HAD>
+__global__ void __launch_bounds__(128)
+had_tiled_kernel(const half* __restrict__ A, uint8_t* __restrict__ out, const half* __restrict__ suh,
+                 int m, int k, int NT)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int bpr = k / 128;
+    if (warp >= m * bpr) return;
+    const int r = warp / bpr, kb = warp % bpr;
+    uint2 raw = *reinterpret_cast<const uint2*>(A + (size_t) r * k + kb * 128 + lane * 4);
+    half2 a = *reinterpret_cast<half2*>(&raw.x), b = *reinterpret_cast<half2*>(&raw.y);
+    if constexpr (HAD)
+    {
+        uint2 scb = *reinterpret_cast<const uint2*>(suh + kb * 128 + lane * 4);
+        a = __hmul2(a, *reinterpret_cast<half2*>(&scb.x));
+        b = __hmul2(b, *reinterpret_cast<half2*>(&scb.y));
+        float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
+        had128_warp(v0, v1, v2, v3, lane);
+        a = __floats2half2_rn(v0 * R_SCALE, v1 * R_SCALE);
+        b = __floats2half2_rn(v2 * R_SCALE, v3 * R_SCALE);
+    }
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    const size_t off = (size_t) kb * NT * 256 + ((((r >> 3) * 16 + (lane >> 1)) * 8 + (r & 7)) * 16) + (lane & 1) * 8;
+    *reinterpret_cast<uint2*>(out + off) = o;
+}
+
+// ---- work partition helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
+__device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
+
+// ---- the kernel -------------------------------------------------------------------------------------------------
+template <int K, int cb>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const TcSmemLayout L = tc_smem_layout(K, p.NT, p.stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    // barrier map: [0,S) w_full  [S,2S) w_empty  [2S,2S+4) a_full  [2S+4,2S+8) a_empty  [2S+8,+2) d_full  [2S+10,+2) d_empty
+    const uint32_t bar0 = smem_u32(bars);
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * S + 4 + s); };
+    auto D_FULL = [&](int s) { return bar0 + 8u * (2 * S + 8 + s); };
+    auto D_EMPTY = [&](int s) { return bar0 + 8u * (2 * S + 10 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (2 * TC_MAX_STAGES + 12));
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    pdl_launch_dependents();
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1)
+    {
+        if (p.tmem_cols == 256) tmem_alloc<256>(smem_u32(tmem_slot)); else tmem_alloc<512>(smem_u32(tmem_slot));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- this CTA's unit range ----
+    const int KB = p.k / 128;
+    const int strips = p.n / 128;
+    const long long U = (long long) KB * strips;
+    const int G = gridDim.x;
+    const long long ubeg = unit_begin(U, G, blockIdx.x), uend = unit_begin(U, G, blockIdx.x + 1);
+    const int n_units = (int) (uend - ubeg);
+    const int tiles_n = p.n / 16;
+    const int a_cols0 = 0;
+    const int d_cols0 = p.a_stages * TC_A_STAGE_COLS;
+
+    if (warp == 0)
+    {
+        // =========================== producer ===========================
+        if (lane == 0)
+        {
+            const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
+            auto issue_w = [&](int u)
+            {
+                const long long g = ubeg + u;
+                const int strip = (int) (g / KB), kb = (int) (g % KB);
+                const int s = u % S;
+                mbar_arrive_expect_tx(W_FULL(s), (uint32_t) (L.w_bytes + p.b_load_bytes));
+                const uint32_t dst = smem_u32(smem + s * L.w_bytes);
+                #pragma unroll
+                for (int r = 0; r < 8; ++r)
+                {
+                    const uint32_t* src = p.B + ((size_t) (kb * 8 + r) * tiles_n + strip * 8) * (8 * K);
+                    bulk_g2s(dst + r * 256 * K, src, 256 * K, W_FULL(s), pol_w);
+                }
+            };
+            auto issue_x = [&](int u)
+            {
+                const long long g = ubeg + u;
+                const int kb = (int) (g % KB);
+                const int s = u % S;
+                bulk_g2s(smem_u32(smem + L.off_b + s * L.b_bytes), p.xh_tiled + (size_t) kb * p.NT * 256,
+                         (uint32_t) p.b_load_bytes, W_FULL(s), pol_x);
+            };
+            const int pre = n_units < S ? n_units : S;
+            for (int u = 0; u < pre; ++u) issue_w(u);           // weights do not depend on the previous kernel
+            pdl_wait();                                          // activations do
+            for (int u = 0; u < pre; ++u) issue_x(u);
+            for (int u = pre; u < n_units; ++u)
+            {
+                mbar_wait(W_EMPTY(u % S), ((u / S) & 1) ^ 1);
+                issue_w(u);
+                issue_x(u);
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp == 1)
+    {
+        // =========================== MMA issuer ===========================
+        if (lane == 0)
+        {
+            const uint32_t idesc = idesc_f16_f32(128, p.NT);
+            int dbuf = 0, dphase = 0, seg_left = 0;
+            uint32_t acc = 0;
+            for (int u = 0; u < n_units; ++u)
+            {
+                const long long g = ubeg + u;
+                const int kb = (int) (g % KB);
+                if (seg_left == 0)
+                {
+                    // new segment: units up to the end of this strip or of this CTA's range
+                    const int to_strip_end = KB - kb;
+                    seg_left = (n_units - u) < to_strip_end ? (n_units - u) : to_strip_end;
+                    mbar_wait(D_EMPTY(dbuf), dphase ^ 1);
+                    tc_fence_after();
+                    acc = 0;
+                }
+                const int s = u % S, as = u % p.a_stages;
+                mbar_wait(W_FULL(s), (u / S) & 1);
+                mbar_wait(A_FULL(as), (u / p.a_stages) & 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + d_cols0 + dbuf * p.NT;
+                const uint32_t a_addr = tmem_base + a_cols0 + as * TC_A_STAGE_COLS;
+                const uint32_t b_addr = smem_u32(smem + L.off_b + s * L.b_bytes);
+                #pragma unroll
+                for (int j = 0; j < 8; ++j)
+                {
+                    mma_f16_ts(d_addr, a_addr + 8 * j, smem_desc(b_addr + j * 256, 128, 2048, 0), idesc, acc);
+                    acc = 1;
+                }
+                tc_commit(A_EMPTY(as));
+                tc_commit(W_EMPTY(s));
+                if (--seg_left == 0)
+                {
+                    tc_commit(D_FULL(dbuf));
+                    if (p.d_bufs == 2) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
+                    else dphase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp >= TC_DEC_WARP0 && warp < TC_DEC_WARP0 + TC_DEC_WARPS)
+    {
+        // =========================== decode ===========================
+        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;
+        const int tl = strip_tile(q, lane), chunk = lane & 7;
+        const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        for (int u = 0; u < n_units; ++u)
+        {
+            const int s = u % S, as = u % p.a_stages;
+            mbar_wait(W_FULL(s), (u / S) & 1);
+            mbar_wait(A_EMPTY(as), ((u / p.a_stages) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
+            #pragma unroll
+            for (int tt = 0; tt < 4; ++tt)
+            {
+                const int t = 2 * tt + h;
+                const uint32_t* cp = wst + (t * 8 + tl) * (8 * K) + chunk * K;
+                uint32_t w[K + 1], o[8];
+                if constexpr (K % 4 == 0)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; j += 4)
+                    {
+                        uint4 v = *reinterpret_cast<const uint4*>(cp + j);
+                        w[1 + j] = v.x; w[2 + j] = v.y; w[3 + j] = v.z; w[4 + j] = v.w;
+                    }
+                }
+                else if constexpr (K % 2 == 0)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; j += 2)
+                    {
+                        uint2 v = *reinterpret_cast<const uint2*>(cp + j);
+                        w[1 + j] = v.x; w[2 + j] = v.y;
+                    }
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; ++j) w[1 + j] = cp[j];
+                }
+                w[0] = __shfl_sync(0xffffffffu, w[K], prev_lane);     // last word of the preceding chunk (cyclic in the tile)
+                if (q & 1) decode16<K, cb, 1>(w, o); else decode16<K, cb, 0>(w, o);
+                tmem_st_32x32b_x8(tmem_base + lane_base + a_cols0 + as * TC_A_STAGE_COLS + 8 * t, o);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
+        }
+    }
+    else if (warp >= TC_EPI_WARP0)
+    {
+        // =========================== epilogue ===========================
+        pdl_wait();                                   // no global write before the previous grid has fully completed
+        const int q = warp & 3;
+        const int et = threadIdx.x - TC_EPI_WARP0 * 32;          // 0..127
+        const int col = strip_col(q, lane);
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        float* tile = reinterpret_cast<float*>(smem + L.off_tile);
+        const size_t esz = p.c_fp32 ? 4 : 2;
+        auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+        const int part_stride = p.NT * 128;
+
+        // rows [c0, c0+16) of one strip: tile (fp32 sums) -> output transform -> C
+        auto emit_rows = [&](int strip, int c0)
+        {
+            epi_bar();
+            for (int j = q; j < 16 && c0 + j < p.m; j += 4)
+                output_row_128(tile + j * 128, (char*) p.C, (size_t) (c0 + j) * p.n + strip * 128,
+                               p.svh ? p.svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
+            epi_bar();
+        };
+
+        int dbuf = 0, dphase = 0;
+        int u = 0;
+        while (u < n_units)
+        {
+            const long long g = ubeg + u;
+            const int strip = (int) (g / KB), kb = (int) (g % KB);
+            const int to_strip_end = KB - kb;
+            const int seg = (n_units - u) < to_strip_end ? (n_units - u) : to_strip_end;
+            const long long gs = (long long) strip * KB;
+            const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + KB - 1);
+            const int n_contrib = c_b - c_a + 1;
+            const bool full = n_contrib == 1;
+            float* my_part = p.ws + (size_t) (2 * blockIdx.x + (ubeg >= gs ? 0 : 1)) * part_stride;
+
+            mbar_wait(D_FULL(dbuf), dphase);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + lane_base + d_cols0 + dbuf * p.NT;
+            for (int c0 = 0; c0 < p.m; c0 += 16)
+            {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(d_addr + c0, r);
+                tc_wait_ld();
+                if (full)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) tile[j * 128 + col] = __uint_as_float(r[j]);
+                    emit_rows(strip, c0);
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.m) my_part[(c0 + j) * 128 + col] = __uint_as_float(r[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(D_EMPTY(dbuf));
+            if (p.d_bufs == 2) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
+            else dphase ^= 1;
+
+            if (!full)
+            {
+                __threadfence();
+                epi_bar();
+                if (et == 0)
+                {
+                    const int old = atomicAdd(&p.counters[strip], 1);
+                    const int last = old == n_contrib - 1;
+                    if (last) p.counters[strip] = 0;          // self-reset for the next launch using this slot
+                    *s_flag = last;
+                }
+                epi_bar();
+                if (*s_flag)
+                {
+                    __threadfence();
+                    for (int c0 = 0; c0 < p.m; c0 += 16)
+                    {
+                        float acc[16];
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                        for (int c = c_a; c <= c_b; ++c)                 // fixed order: deterministic
+                        {
+                            const float* part = p.ws + (size_t) (2 * c + (unit_begin(U, G, c) >= gs ? 0 : 1)) * part_stride;
+                            #pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.m) acc[j] += __ldcg(part + (c0 + j) * 128 + col);
+                        }
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) tile[j * 128 + col] = acc[j];
+                        emit_rows(strip, c0);
+                    }
+                }
+                epi_bar();
+            }
+            u += seg;
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+    {
+        tc_fence_after();
+        if (p.tmem_cols == 256) tmem_dealloc<256>(tmem_base); else tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+
+template <int K, int cb>
+static cudaError_t tc_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p)
+{
+    static bool attr_set[32] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_set[dev & 31])
+    {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<K, cb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 31] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<K, cb>, p);
+}
+
+template <int K, int cb>
+static void tc_launch_v(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, cudaError_t* err)
+{
+    *err = tc_launch<K, cb>(stream, grid, smem_bytes, p);
+}
+
+bool gemm_tc_supported(const GemmArgs& a)
+{
+    return a.k >= 128 && a.n >= 128 && a.k % 128 == 0 && a.n % 128 == 0 && a.m >= 1;
+}
+
+static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, const half* suh, int m, int k, int NT)
+{
+    const int warps = m * (k / 128);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((warps + 3) / 4); cfg.blockDim = dim3(128); cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = suh ? cudaLaunchKernelEx(&cfg, had_tiled_kernel<true>, A, out, suh, m, k, NT)
+                        : cudaLaunchKernelEx(&cfg, had_tiled_kernel<false>, A, out, suh, m, k, NT);
+    count_launch();
+    EXL3B_CUDA(e);
+    return 0;
+}
+
+int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
+{
+    const size_t esz = a.c_fp32 ? 4 : 2;
+    for (int m0 = 0; m0 < a.m; m0 += 256)
+    {
+        const int m = a.m - m0 < 256 ? a.m - m0 : 256;
+        const int NT = (m + 15) / 16 * 16;
+        const int slot = ctx->next_slot();
+        const size_t xh_bytes = (size_t) (a.k / 128) * NT * 256;
+        int r = ensure_xh_tiled(ctx, xh_bytes); if (r) return r;
+        uint8_t* xh_tiled = ctx->xh_tiled + (size_t) (slot % DevCtx::XH_SLOTS) * ctx->xh_tiled_slot_bytes;
+        r = launch_had_tiled(stream, a.A + (size_t) m0 * a.k, xh_tiled, a.suh, m, a.k, NT); if (r) return r;
+
+        TcParams p{};
+        p.xh_tiled = xh_tiled; p.B = a.B; p.C = (char*) a.C + (size_t) m0 * a.n * esz; p.svh = a.svh;
+        p.m = m; p.k = a.k; p.n = a.n; p.NT = NT; p.c_fp32 = a.c_fp32; p.out_scale = a.out_scale;
+        p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
+        const bool small = NT <= 32;
+        p.tmem_cols = small ? 256 : 512;
+        p.a_stages = small ? 3 : 4;
+        p.d_bufs = NT <= 128 ? 2 : 1;
+        p.b_load_bytes = m <= 8 ? 2048 : NT * 256;
+        const int stage_bytes = 2048 * a.K + NT * 256;
+        const int budget = small ? 96 * 1024 : 180 * 1024;
+        int stages = budget / stage_bytes;
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        if (stages < 2) stages = 2;
+        p.stages = stages;
+        const TcSmemLayout L = tc_smem_layout(a.K, NT, stages);
+        EXL3B_CHECK(L.total <= 200 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: shared-memory budget exceeded");
+
+        const long long U = (long long) (a.k / 128) * (a.n / 128);
+        int grid = ctx->num_sms;
+        if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
+        if (grid > U) grid = (int) U;
+        EXL3B_CHECK((size_t) 2 * grid * NT * 128 * 4 <= DevCtx::WS_BYTES_PER_SLOT, EXL3B_ERR_UNSUPPORTED,
+                    "exl3_gemm: split-K workspace too small");
+        EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+
+        cudaError_t err = cudaSuccess;
+        EXL3B_DISPATCH_K_CB(tc_launch_v, a.K, a.cb, stream, grid, L.total, p, &err);
+        count_launch();
+        EXL3B_CUDA(err);
+    }
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return EXL3B_TAG_TC;
+}
+
+// dense hgemm on tcgen05: lands with the prefill work
+bool hgemm_tc_supported(int, int, int, int64_t) { return false; }
+int launch_hgemm_tc(cudaStream_t, const half*, const half*, void*, int, int, int, bool, int64_t)
+{
+    return fail(EXL3B_ERR_UNSUPPORTED, "tcgen05 hgemm not built");
+}
+
+}  // namespace exl3b

@@ -41,15 +41,34 @@ def main(mode):
         for i in range(10):
             tag = gemm(A, Bs[i % copies], C, su, Ah, sv)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 60
-        e0.record()
-        for i in range(iters):
-            gemm(A, Bs[i % copies], C, su, Ah, sv)
-        e1.record(); e1.synchronize()
+        # kernels only: replay a CUDA graph of the 60 calls (the reference's own decode path replays graphs,
+        # libtorch/mlp.cpp:93-147); eager launches measure host launch overhead instead
+        graph, mode_used = None, "eager"
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=st):
+                    for i in range(iters):
+                        gemm(A, Bs[i % copies], C, su, Ah, sv)
+            mode_used = "graph"
+        except Exception as ex:
+            print("graph capture failed:", type(ex).__name__, str(ex)[:200], flush=True)
+            graph = None
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if graph is not None:
+            graph.replay(); torch.cuda.synchronize()
+            e0.record(); graph.replay(); e1.record(); e1.synchronize()
+        else:
+            e0.record()
+            for i in range(iters):
+                gemm(A, Bs[i % copies], C, su, Ah, sv)
+            e1.record(); e1.synchronize()
         us = e0.elapsed_time(e1) * 1000 / iters
         alg = nbytes + 2 * m * k + 2 * m * n + 2 * (k + n)
-        res.append(dict(shape=name, k=k, n=n, K=K, m=m, us=us, gbps=alg / us / 1e3, tag=int(tag) if tag is not None else None))
+        res.append(dict(timing=mode_used, shape=name, k=k, n=n, K=K, m=m, us=us, gbps=alg / us / 1e3, tag=int(tag) if tag is not None else None))
         print(mode, res[-1], flush=True)
         del Bs
         torch.cuda.empty_cache()

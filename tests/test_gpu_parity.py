@@ -93,29 +93,39 @@ def test_had_r_128_bitexact(cuda, dt, mode):
     assert (xi.cpu().numpy().view(view) == orc.had_r_128(x).view(view)).all()
 
 
+@pytest.fixture(params=["tc", "simt"])
+def gemm_path(request):
+    """Run the test once per kernel path: tcgen05 (default product path) and the CUDA-core path."""
+    from exllamav3_b200 import ext
+    prev = ext.set_gemm_path(ext.EXL3B_TAG_TC if request.param == "tc" else ext.EXL3B_TAG_SIMT)
+    yield request.param
+    ext.set_gemm_path(prev)
+
+
 @pytest.mark.parametrize("K,cb", [(1, 2), (2, 2), (3, 0), (4, 2), (4, 0), (4, 1), (5, 2), (6, 2), (7, 1), (8, 2)])
 @pytest.mark.parametrize("m", [1, 5, 16, 17])
-def test_gemm_vs_oracle(cuda, K, cb, m):
+def test_gemm_vs_oracle(cuda, gemm_path, K, cb, m):
     from exllamav3_b200 import ext
     k, n = 512, 384
     tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
     ref = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
     for fp32 in (False, True):
         y, xh, tag = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, fp32)
-        assert tag in (ext.EXL3B_TAG_SIMT, ext.EXL3B_TAG_TC)
+        assert tag == (ext.EXL3B_TAG_TC if gemm_path == "tc" else ext.EXL3B_TAG_SIMT)
         assert not np.isnan(y.astype(np.float32)).any()
-        xh_ref = orc.had_r_128(x, pre_scale=suh)
-        assert (xh.view(np.uint16) == xh_ref.view(np.uint16)).all()          # input transform bit-exact
+        if gemm_path == "simt":      # the tcgen05 path keeps its transformed input in a private tiled buffer
+            xh_ref = orc.had_r_128(x, pre_scale=suh)
+            assert (xh.view(np.uint16) == xh_ref.view(np.uint16)).all()      # input transform bit-exact
         mx, rms = rel_err(y, ref)
         ulp = 2.0 ** -10 if not fp32 else 0.0
         assert mx <= 2e-3 + ulp, (K, cb, m, fp32, mx)
         assert rms <= 1e-3, (K, cb, m, fp32, rms)
 
 
-def test_gemm_without_scratch_and_ragged_rows(cuda):
+def test_gemm_without_scratch_and_ragged_rows(cuda, gemm_path):
     from exllamav3_b200 import ext
     K, cb, k, n = 4, 2, 256, 256
-    for m in (1, 3, 31, 33, 144):          # rows up to the reconstruct threshold (modules/quant/exl3.py:10)
+    for m in (1, 3, 8, 9, 31, 33, 144, 300):          # rows up to the reconstruct threshold (modules/quant/exl3.py:10)
         tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
         ref = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
         y, _, _ = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, True, a_had=False)
@@ -129,7 +139,7 @@ def test_gemm_without_scratch_and_ragged_rows(cuda):
     assert mx <= 3e-3 and rms <= 1e-3
 
 
-def test_gemm_vs_reference_cuda_golden(cuda):
+def test_gemm_vs_reference_cuda_golden(cuda, gemm_path):
     p = os.path.join(GOLDEN, "ref_gpu.npz")
     if not os.path.exists(p):
         pytest.skip("tests/golden/ref_gpu.npz not generated yet")
@@ -139,7 +149,8 @@ def test_gemm_vs_reference_cuda_golden(cuda):
         tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
         key = f"gemm_{m}_{k}_{n}_{K}_{cb}_{int(fp32)}"
         y, xh, _ = run_gemm(ext, cuda, x, tr, suh, svh, K, cb, fp32)
-        assert (xh.view(np.uint16) == g[key + "_xh"].view(np.uint16)).all(), key
+        if gemm_path == "simt":
+            assert (xh.view(np.uint16) == g[key + "_xh"].view(np.uint16)).all(), key
         mx, rms = rel_err(y, g[key])
         assert mx <= 4e-3 and rms <= 2e-3, (key, mx, rms)
     for (K, cb, k, n) in gg.reconstruct_cases():
@@ -263,6 +274,24 @@ def test_mgemm_modes(cuda):
         assert rel_err(C[0].cpu().numpy(), ref[0])[0] <= tol
         if golden is not None:
             assert rel_err(C[0].cpu().numpy(), golden[f"mgemm_d_{int(fp32)}"])[0] <= 5e-3
+
+
+def test_tc_determinism_and_stream_k(cuda):
+    """Split-K partials are combined in a fixed order: repeated launches are bit-identical; shapes chosen so that
+    strips are split across CTAs (k large, n small) and so that CTAs span several strips (n large)."""
+    from exllamav3_b200 import ext
+    prev = ext.set_gemm_path(ext.EXL3B_TAG_TC)
+    try:
+        for (k, n, m) in ((8192, 128, 1), (4096, 256, 3), (128, 8192, 2), (1024, 2048, 16)):
+            tr, suh, svh, x = orc.make_synthetic(k, n, 4, m=m)
+            ref = orc.exl3_gemm_f64(x, tr, suh, svh, 4, 2)
+            outs = [run_gemm(ext, cuda, x, tr, suh, svh, 4, 2, True)[0] for _ in range(3)]
+            assert (outs[0].view(np.uint32) == outs[1].view(np.uint32)).all()
+            assert (outs[0].view(np.uint32) == outs[2].view(np.uint32)).all()
+            mx, rms = rel_err(outs[0], ref)
+            assert mx <= 2e-3 and rms <= 1e-3, (k, n, m, mx, rms)
+    finally:
+        ext.set_gemm_path(prev)
 
 
 def test_full_size_properties(cuda):
