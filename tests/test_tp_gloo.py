@@ -1,0 +1,71 @@
+"""
+N > 1 host logic on CPU: world_size-2 `gloo` processes build column / row shards with the reference's slicing rules
+and run the collective plumbing of exllamav3_b200.tp.  There is no GPU here, so each rank's local matmul is computed
+by the oracle (checker) on that rank's SHARD tensors -- what is under test is the sharding + all-reduce logic:
+column shards concatenate to, and row shards sum to, the unsharded result.
+"""
+import os, sys
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from exllamav3_b200 import LinearEXL3, tp
+        from oracle import exl3_oracle as orc
+        k, n, K, cb, m = 512, 768, 4, 2, 3
+        tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+        lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr),
+                         mul1=torch.zeros((), dtype=torch.int))
+        full = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
+
+        def local_gemm(shard, x_local):       # oracle stands in for the CUDA kernel on this GPU-less box
+            y = orc.exl3_gemm_f64(x_local, shard.trellis.numpy(), shard.suh.numpy(), shard.svh.numpy(), shard.K, cb)
+            return torch.from_numpy(y)
+
+        # column parallel: no communication, gather only to verify
+        cs = tp.column_shard(lin, rank, world)
+        yc = local_gemm(cs, x)
+        parts = [torch.empty_like(yc) for _ in range(world)]
+        dist.all_gather(parts, yc)
+        err_c = float((torch.cat(parts, dim=1) - torch.from_numpy(full)).abs().max())
+
+        # row parallel: partial with full epilogue on every rank, one all-reduce
+        rs = tp.row_shard(lin, rank, world)
+        first, last = tp.split_ranges(k, world)[rank]
+        yr = tp.all_reduce(local_gemm(rs, np.ascontiguousarray(x[:, first:last])))
+        err_r = float((yr - torch.from_numpy(full)).abs().max())
+        ret[rank] = (err_c, err_r, cs.out_features, rs.in_features)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_column_and_row_sharding_world2():
+    world, port = 2, 29517 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        err_c, err_r, out_f, in_f = ret[rank]
+        assert out_f == 384 and in_f == 256
+        assert err_c < 1e-9, err_c            # identical math, just partitioned along n
+        assert err_r < 2e-3, err_r            # fp16 rounding of xh is per 128-block => partial sums differ only in fp64 order
+
+
+def test_split_ranges():
+    from exllamav3_b200 import tp
+    assert tp.split_ranges(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
+    assert tp.split_ranges(14336, 8)[0] == (0, 1792) and tp.split_ranges(14336, 8)[-1][1] == 14336
+    r = tp.split_ranges(1024, 3)          # uneven: 8 units -> 3, 3, 2
+    assert [b - a for a, b in r] == [384, 384, 256]
+    with pytest.raises(AssertionError):
+        tp.split_ranges(256, 4)
