@@ -87,6 +87,7 @@ int ensure_xh_tiled(DevCtx* ctx, size_t bytes_per_slot)
 
 }  // namespace exl3b
 
+namespace exl3b { void tc_set_debug_buffer(unsigned long long* d); void tc_set_knob(int k); }
 using namespace exl3b;
 
 extern "C" {
@@ -98,6 +99,10 @@ const char* exl3b_last_error(void) { return g_err.c_str(); }
 int64_t exl3b_launch_count(void) { return g_launches.load(); }
 
 int exl3b_set_gemm_path(int tag) { return g_force_path.exchange(tag); }
+
+// bring-up aid (not in the public header): per-CTA %globaltimer stamps of the tcgen05 kernel, 16 x u64 per CTA
+void exl3b_debug_tc_timeline(void* dev_buf) { exl3b::tc_set_debug_buffer((unsigned long long*) dev_buf); }
+void exl3b_debug_tc_knob(int knob) { exl3b::tc_set_knob(knob); }
 
 int exl3b_num_sms(int device)
 {
@@ -184,9 +189,15 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
     g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f;
     g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
 
+    // path selection: auto = int8 tensor-core codebook path for mul1 at m <= 4 (like the reference, whose default for
+    // mul1 at m <= 2 is its int8 GEMV, exl3_gemm.cu:182-186), else the bit-exact tcgen05 path
     int path = g_force_path.load();
+    if (path == EXL3B_TAG_TC_I8)
+        EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4)");
     if (path == EXL3B_TAG_TC)
         EXL3B_CHECK(gemm_tc_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: tcgen05 path forced but shape unsupported");
+    if ((path == 0 || path == EXL3B_TAG_TC_I8) && gemm_tc_i8_supported(g))
+        return launch_gemm_tc_i8(stream, ctx, g);
     if (path != EXL3B_TAG_SIMT && gemm_tc_supported(g))
         return launch_gemm_tc(stream, ctx, g);
     return launch_gemm_simt(stream, ctx, g);

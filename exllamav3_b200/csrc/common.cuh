@@ -82,6 +82,8 @@ struct GemmArgs
 int launch_gemm_simt(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 bool gemm_tc_supported(const GemmArgs& a);
+int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+bool gemm_tc_i8_supported(const GemmArgs& a);
 
 struct MGemmArgs
 {

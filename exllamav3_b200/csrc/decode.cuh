@@ -115,6 +115,51 @@ __device__ __forceinline__ void decode16(const uint32_t (&w)[K + 1], uint32_t (&
     decode4<K, cb, HALF, 3>(w, out[3], out[7]);
 }
 
+// ---- int8 tensor-core codebook path (mul1 only) -----------------------------------------------------------------
+// The mul1 value is k_inv * (1024 + bytesum(state * 0x83DCD12D)) + k_bias (codebook.cuh:77-89).  Instead of summing the
+// four product bytes on the IMAD pipe (IDP.4A shares it, profiles/r01_microbench_pipes.log) the product word itself
+// becomes four unsigned 8-bit K-elements of a tcgen05 kind::i8 operand and the tensor core does the byte sum while
+// contracting with the (4x replicated) int8 activation digits.  Cost per weight: window extraction + ONE IMAD.
+// out[k] = state(k) * 0x83DCD12D for the 16 k-rows of the thread's tile column, in k order.
+template <int K, int HALF, int J>
+__device__ __forceinline__ void products4(const uint32_t (&w)[K + 1], uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3)
+{
+    constexpr int P = 8 * J + 4 * HALF;
+    uint32_t s0, s1, s2, s3;
+    if constexpr (K == 4)
+    {
+        // the four windows live in one 32-bit span ending at chunk bit 32J + 16 (HALF 0) or 32J + 32 (HALF 1)
+        const uint32_t v = HALF == 0 ? __funnelshift_r(w[1 + J], w[J], 16) : w[1 + J];
+        const uint32_t t = v >> 4;
+        s3 = prmt(v, 0u, 0x4410);          // v & 0xffff
+        s1 = prmt(v, 0u, 0x4421);          // (v >> 8) & 0xffff
+        s2 = prmt(t, 0u, 0x4410);          // (v >> 4) & 0xffff
+        s0 = prmt(t, 0u, 0x4421);          // (v >> 12) & 0xffff
+    }
+    else if constexpr (K == 8)
+    {
+        // byte-aligned windows: positions end at chunk bytes P+1 .. P+4
+        s0 = window16<K, (P + 1) * K>(w); s1 = window16<K, (P + 2) * K>(w);
+        s2 = window16<K, (P + 3) * K>(w); s3 = window16<K, (P + 4) * K>(w);
+    }
+    else
+    {
+        s0 = window16<K, (P + 1) * K>(w); s1 = window16<K, (P + 2) * K>(w);
+        s2 = window16<K, (P + 3) * K>(w); s3 = window16<K, (P + 4) * K>(w);
+    }
+    x0 = s0 * 0x83DCD12Du; x1 = s1 * 0x83DCD12Du; x2 = s2 * 0x83DCD12Du; x3 = s3 * 0x83DCD12Du;
+}
+
+template <int K, int HALF>
+__device__ __forceinline__ void decode16_i8(const uint32_t (&w)[K + 1], uint32_t (&out)[16])
+{
+    // positions 8J + 4*HALF + {0,1,2,3} -> k = 2J, 2J+1, 2J+8, 2J+9
+    products4<K, HALF, 0>(w, out[0], out[1], out[8], out[9]);
+    products4<K, HALF, 1>(w, out[2], out[3], out[10], out[11]);
+    products4<K, HALF, 2>(w, out[4], out[5], out[12], out[13]);
+    products4<K, HALF, 3>(w, out[6], out[7], out[14], out[15]);
+}
+
 // Thread -> column mapping inside a 128-column strip (8 tiles).  q = lane quarter (warp index % 4), i = lane.
 //   tile-in-strip = 4*(q>>1) + (i>>3), chunk = i&7, half = q&1   =>   n_local = 16*tile + 8*half + chunk
 __device__ __forceinline__ int strip_tile(int q, int i)  { return 4 * (q >> 1) + (i >> 3); }

@@ -7,15 +7,17 @@
 //     activations are the N = 16..256 operand, so the weight stream is decoded exactly ONCE for any m <= 256
 //     (the reference re-streams and re-decodes B per 16-row slab, exl3_gemm_kernel.cuh:37-50).
 //   * persistent stream-K over work units of 128(k) x 128(n) weights: CTA c owns units [U*c/G, U*(c+1)/G), k fastest.
-//   * warp-specialised, 512 threads:
+//   * warp-specialised, 768 threads:
 //        warp 0      producer: cp.async.bulk (TMA engine) of the raw trellis rows + the activation tile into an
 //                    mbarrier ring (weights prefetch starts BEFORE griddepcontrol.wait: PDL overlap with the
 //                    previous kernel's tail)
 //        warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::f16 with A read from TMEM and B from
 //                    shared memory, accumulators in TMEM; also owns TMEM alloc/dealloc
-//        warps 4-11  decode: LDS the packed chunk, decode 16 weights per thread per 16x16 tile, tcgen05.st them
+//        warps 2-3   (m <= 8) input transform fused in-kernel: A*suh -> 128-point Hadamard -> fp16 core-matrix tile
+//                    written straight into the activation stage (no separate transform launch on the decode path)
+//        warps 4-19  decode: LDS the packed chunk, decode 16 weights per thread per 16x16 tile, tcgen05.st them
 //                    straight into the TMEM A-operand stage (decoded weights never touch shared memory)
-//        warps 12-15 epilogue: tcgen05.ld the accumulators, split-K combine through a global workspace
+//        warps 20-23 epilogue: tcgen05.ld the accumulators, split-K combine through a global workspace
 //                    (last-arriver reduces in fixed order => deterministic), output Hadamard + svh, store
 //   * activations arrive pre-tiled in the no-swizzle K-major core-matrix layout tcgen05 wants, written by the
 //     input-transform kernel (fused suh scale + 128-point Hadamard), so the B tile is one contiguous bulk copy.
@@ -24,53 +26,13 @@
 #include "common.cuh"
 #include "decode.cuh"
 #include "epilogue.cuh"
-#include "ptx.cuh"
+#include "tc_common.cuh"
+#include <unordered_map>
+#include <mutex>
 
 namespace exl3b {
 
 using namespace ptx;
-
-constexpr int TC_THREADS = 512;
-constexpr int TC_DEC_WARP0 = 4;
-constexpr int TC_DEC_WARPS = 8;
-constexpr int TC_EPI_WARP0 = 12;
-constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_A_STAGE_COLS = 64;          // 128 k-values x fp16, 2 per 32-bit TMEM column
-
-struct TcParams
-{
-    const uint8_t* xh_tiled;     // [k/128][NT/8][16][8][8] fp16 (core-matrix tiles)
-    const uint32_t* B;
-    void* C;
-    const half* svh;
-    int m, k, n, NT;
-    int c_fp32;
-    float out_scale;
-    float* ws;
-    int* counters;
-    int stages;                  // smem ring depth
-    int b_load_bytes;            // bytes of the activation tile copied per unit
-    int a_stages;                // TMEM A-operand stages (3 or 4)
-    int d_bufs;                  // TMEM accumulator buffers (1 or 2)
-    int tmem_cols;               // 256 or 512
-};
-
-struct TcSmemLayout
-{
-    int w_bytes, b_bytes, off_b, off_tile, off_bars, total;
-};
-
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int K, int NT, int stages)
-{
-    TcSmemLayout L;
-    L.w_bytes = 2048 * K;
-    L.b_bytes = NT * 256;
-    L.off_b = stages * L.w_bytes;
-    L.off_tile = L.off_b + stages * L.b_bytes;
-    L.off_bars = L.off_tile + 16 * 128 * 4;
-    L.total = L.off_bars + 512;
-    return L;
-}
 
 // ---- input transform into the tiled activation layout ---------------------------------------------------------
 template <bool HAD>
@@ -101,37 +63,39 @@ had_tiled_kernel(const half* __restrict__ A, uint8_t* __restrict__ out, const ha
     *reinterpret_cast<uint2*>(out + off) = o;
 }
 
-// ---- work partition helpers -------------------------------------------------------------------------------------
-__device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
-__device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
-
 // ---- the kernel -------------------------------------------------------------------------------------------------
 template <int K, int cb>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const TcParams p)
+gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const TcSmemLayout L = tc_smem_layout(K, p.NT, p.stages);
+    const TcSmemLayout L = tc_smem_layout(K, p.b_bytes, p.stages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
-    // barrier map: [0,S) w_full  [S,2S) w_empty  [2S,2S+4) a_full  [2S+4,2S+8) a_empty  [2S+8,+2) d_full  [2S+10,+2) d_empty
+    // barrier map: [0,S) w_full  [S,2S) w_empty  [2S,3S) x_full  then a_full[4] a_empty[4] d_full[2] d_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
-    auto A_FULL = [&](int s) { return bar0 + 8u * (2 * S + s); };
-    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * S + 4 + s); };
-    auto D_FULL = [&](int s) { return bar0 + 8u * (2 * S + 8 + s); };
-    auto D_EMPTY = [&](int s) { return bar0 + 8u * (2 * S + 10 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (2 * TC_MAX_STAGES + 12));
+    auto X_FULL = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (3 * S + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 4 + s); };
+    auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
+    auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
+    auto stamp = [&](int slot)
+    {
+        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[blockIdx.x * 16 + slot] = t; }
+    };
+    if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
         fence_barrier_init();
@@ -144,6 +108,7 @@ gemm_tc_kernel(const TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(1);
 
     // ---- this CTA's unit range ----
     const int KB = p.k / 128;
@@ -159,40 +124,49 @@ gemm_tc_kernel(const TcParams p)
     if (warp == 0)
     {
         // =========================== producer ===========================
-        if (lane == 0)
+        // whole warp runs the loop (uniform control flow -> uniform-register operands); one elected lane issues
         {
+            if (elect_one()) prefetch_tmap(&tmap_w);
             const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
-            auto issue_w = [&](int u)
+            const uint32_t w_smem0 = smem_u32(smem), x_smem0 = smem_u32(smem + L.off_b);
+            auto issue_w = [&](int s, int strip, int kb)
             {
-                const long long g = ubeg + u;
-                const int strip = (int) (g / KB), kb = (int) (g % KB);
-                const int s = u % S;
-                mbar_arrive_expect_tx(W_FULL(s), (uint32_t) (L.w_bytes + p.b_load_bytes));
-                const uint32_t dst = smem_u32(smem + s * L.w_bytes);
-                #pragma unroll
-                for (int r = 0; r < 8; ++r)
+                if (elect_one())
                 {
-                    const uint32_t* src = p.B + ((size_t) (kb * 8 + r) * tiles_n + strip * 8) * (8 * K);
-                    bulk_g2s(dst + r * 256 * K, src, 256 * K, W_FULL(s), pol_w);
+                    mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
+                    // one 2-D TMA box per unit: 8 tile-rows x (256*K bytes = 32*K uint64) of the trellis
+                    tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
                 }
             };
-            auto issue_x = [&](int u)
+            auto issue_x = [&](int s, int kb)
             {
-                const long long g = ubeg + u;
-                const int kb = (int) (g % KB);
-                const int s = u % S;
-                bulk_g2s(smem_u32(smem + L.off_b + s * L.b_bytes), p.xh_tiled + (size_t) kb * p.NT * 256,
-                         (uint32_t) p.b_load_bytes, W_FULL(s), pol_x);
+                if (elect_one())
+                {
+                    mbar_arrive_expect_tx(X_FULL(s), (uint32_t) p.b_load_bytes);
+                    bulk_g2s(x_smem0 + s * L.b_bytes, p.xh_tiled + (size_t) kb * p.NT * 256,
+                             (uint32_t) p.b_load_bytes, X_FULL(s), pol_x);
+                }
             };
             const int pre = n_units < S ? n_units : S;
-            for (int u = 0; u < pre; ++u) issue_w(u);           // weights do not depend on the previous kernel
-            pdl_wait();                                          // activations do
-            for (int u = 0; u < pre; ++u) issue_x(u);
+            const int strip0 = (int) (ubeg / KB), kb0 = (int) (ubeg % KB);
+            int strip = strip0, kb = kb0;
+            auto next_unit = [&] { if (++kb == KB) { kb = 0; ++strip; } };
+            for (int u = 0; u < pre; ++u) { issue_w(u, strip, kb); next_unit(); }   // weights never depend on the previous kernel
+            const bool fused_x = p.A_raw != nullptr;
+            if (!fused_x)
+            {
+                pdl_wait();                                                          // activations do
+                int kbx = kb0; for (int u = 0; u < pre; ++u) { issue_x(u, kbx); if (++kbx == KB) kbx = 0; }
+            }
+            if (lane == 0) stamp(2);
+            int s = (pre == S) ? 0 : pre, ph = (pre == S) ? 1 : 0;                   // ring position of unit `pre`
             for (int u = pre; u < n_units; ++u)
             {
-                mbar_wait(W_EMPTY(u % S), ((u / S) & 1) ^ 1);
-                issue_w(u);
-                issue_x(u);
+                mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+                issue_w(s, strip, kb);
+                if (!fused_x) issue_x(s, kb);
+                next_unit();
+                if (++s == S) { s = 0; ph ^= 1; }
             }
         }
         __syncwarp();
@@ -200,76 +174,132 @@ gemm_tc_kernel(const TcParams p)
     else if (warp == 1)
     {
         // =========================== MMA issuer ===========================
-        if (lane == 0)
+        // whole warp runs the loop; one elected lane issues the MMAs and their commits
         {
             const uint32_t idesc = idesc_f16_f32(128, p.NT);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t x_smem0 = smem_u32(smem + L.off_b);
+            // descriptor template: LBO 128 B, SBO 2048 B, version 1, no swizzle; the start address goes in bits 0..13
+            const uint64_t desc_hi = smem_desc(0, 128, 2048, 0);
             int dbuf = 0, dphase = 0, seg_left = 0;
             uint32_t acc = 0;
+            int kb = (int) (ubeg % KB);
+            int s = 0, sph = 0, as = 0, aph = 0;
             for (int u = 0; u < n_units; ++u)
             {
-                const long long g = ubeg + u;
-                const int kb = (int) (g % KB);
                 if (seg_left == 0)
                 {
                     // new segment: units up to the end of this strip or of this CTA's range
                     const int to_strip_end = KB - kb;
                     seg_left = (n_units - u) < to_strip_end ? (n_units - u) : to_strip_end;
                     mbar_wait(D_EMPTY(dbuf), dphase ^ 1);
-                    tc_fence_after();
                     acc = 0;
                 }
-                const int s = u % S, as = u % p.a_stages;
-                mbar_wait(W_FULL(s), (u / S) & 1);
-                mbar_wait(A_FULL(as), (u / p.a_stages) & 1);
+                mbar_wait(X_FULL(s), sph);
+                mbar_wait(A_FULL(as), aph);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + d_cols0 + dbuf * p.NT;
-                const uint32_t a_addr = tmem_base + a_cols0 + as * TC_A_STAGE_COLS;
-                const uint32_t b_addr = smem_u32(smem + L.off_b + s * L.b_bytes);
-                #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                if (u == 0 && lane == 0) stamp(5);
+                const uint32_t d_addr = tb + d_cols0 + dbuf * p.NT;
+                const uint32_t a_addr = tb + a_cols0 + as * TC_A_STAGE_COLS;
+                const uint32_t b_addr = x_smem0 + s * L.b_bytes;
+                --seg_left;
+                if (elect_one())
                 {
-                    mma_f16_ts(d_addr, a_addr + 8 * j, smem_desc(b_addr + j * 256, 128, 2048, 0), idesc, acc);
-                    acc = 1;
+                    if (!(p.knob & 4))
+                    {
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                        {
+                            mma_f16_ts(d_addr, a_addr + 8 * j, desc_hi | (uint64_t) (((b_addr + j * 256) >> 4) & 0x3fff),
+                                       idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc_commit(A_EMPTY(as));
+                    tc_commit(W_EMPTY(s));
+                    if (seg_left == 0) tc_commit(D_FULL(dbuf));
                 }
-                tc_commit(A_EMPTY(as));
-                tc_commit(W_EMPTY(s));
-                if (--seg_left == 0)
+                acc = 1;
+                __syncwarp();
+                if (seg_left == 0)
                 {
-                    tc_commit(D_FULL(dbuf));
                     if (p.d_bufs == 2) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
                     else dphase ^= 1;
                 }
+                if (++kb == KB) kb = 0;
+                if (++s == S) { s = 0; sph ^= 1; }
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
             }
+            if (lane == 0) stamp(6);
         }
         __syncwarp();
+    }
+    else if (warp < TC_DEC_WARP0)
+    {
+        // =========================== fused input transform (m <= 8) ===========================
+        if (p.A_raw != nullptr)
+        {
+            pdl_wait();                                  // A is produced by the previous kernel
+            const int xw = warp - TC_XF_WARP0;           // 0 / 1: units of alternating parity
+            int kb = (int) ((ubeg + xw) % KB);
+            int s = xw % S, ph = 0;
+            if (xw >= S) { s = 0; ph = 1; }              // S >= 2 always
+            const int kstep = 2 % KB;
+            for (int u = xw; u < n_units; u += 2)
+            {
+                mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+                uint8_t* dst = smem + L.off_b + s * L.b_bytes;
+                const uint2 scb = p.suh ? *reinterpret_cast<const uint2*>(p.suh + kb * 128 + lane * 4) : make_uint2(0, 0);
+                for (int r = 0; r < p.m; ++r)
+                {
+                    uint2 raw = *reinterpret_cast<const uint2*>(p.A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
+                    half2 a = *reinterpret_cast<half2*>(&raw.x), b = *reinterpret_cast<half2*>(&raw.y);
+                    if (p.suh)
+                    {
+                        a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
+                        b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
+                        float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
+                        had128_warp(v0, v1, v2, v3, lane);
+                        a = __floats2half2_rn(v0 * R_SCALE, v1 * R_SCALE);
+                        b = __floats2half2_rn(v2 * R_SCALE, v3 * R_SCALE);
+                    }
+                    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+                    *reinterpret_cast<uint2*>(dst + ((((r >> 3) * 16 + (lane >> 1)) * 8 + (r & 7)) * 16) + (lane & 1) * 8) = o;
+                }
+                fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(X_FULL(s));
+                kb += kstep; if (kb >= KB) kb -= KB;
+                s += 2; if (s >= S) { s -= S; ph ^= 1; }
+            }
+        }
     }
     else if (warp >= TC_DEC_WARP0 && warp < TC_DEC_WARP0 + TC_DEC_WARPS)
     {
         // =========================== decode ===========================
-        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;
+        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;              // h = 0..3
         const int tl = strip_tile(q, lane), chunk = lane & 7;
         const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        int s = 0, sph = 0, as = 0, aph = 0;
         for (int u = 0; u < n_units; ++u)
         {
-            const int s = u % S, as = u % p.a_stages;
-            mbar_wait(W_FULL(s), (u / S) & 1);
-            mbar_wait(A_EMPTY(as), ((u / p.a_stages) & 1) ^ 1);
-            tc_fence_after();
+            mbar_wait(W_FULL(s), sph);
+            if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
             const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
+            uint32_t w[TC_DEC_TILES][K + 1];
             #pragma unroll
-            for (int tt = 0; tt < 4; ++tt)
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)          // issue all shared-memory loads of this unit up front
             {
-                const int t = 2 * tt + h;
+                const int t = 4 * tt + h;
                 const uint32_t* cp = wst + (t * 8 + tl) * (8 * K) + chunk * K;
-                uint32_t w[K + 1], o[8];
                 if constexpr (K % 4 == 0)
                 {
                     #pragma unroll
                     for (int j = 0; j < K; j += 4)
                     {
                         uint4 v = *reinterpret_cast<const uint4*>(cp + j);
-                        w[1 + j] = v.x; w[2 + j] = v.y; w[3 + j] = v.z; w[4 + j] = v.w;
+                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y; w[tt][3 + j] = v.z; w[tt][4 + j] = v.w;
                     }
                 }
                 else if constexpr (K % 2 == 0)
@@ -278,22 +308,42 @@ gemm_tc_kernel(const TcParams p)
                     for (int j = 0; j < K; j += 2)
                     {
                         uint2 v = *reinterpret_cast<const uint2*>(cp + j);
-                        w[1 + j] = v.x; w[2 + j] = v.y;
+                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y;
                     }
                 }
                 else
                 {
                     #pragma unroll
-                    for (int j = 0; j < K; ++j) w[1 + j] = cp[j];
+                    for (int j = 0; j < K; ++j) w[tt][1 + j] = cp[j];
                 }
-                w[0] = __shfl_sync(0xffffffffu, w[K], prev_lane);     // last word of the preceding chunk (cyclic in the tile)
-                if (q & 1) decode16<K, cb, 1>(w, o); else decode16<K, cb, 0>(w, o);
-                tmem_st_32x32b_x8(tmem_base + lane_base + a_cols0 + as * TC_A_STAGE_COLS + 8 * t, o);
+            }
+            #pragma unroll
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)          // last word of the preceding chunk (cyclic inside the tile)
+                w[tt][0] = __shfl_sync(0xffffffffu, w[tt][K], prev_lane);
+            mbar_wait(A_EMPTY(as), aph ^ 1);
+            tc_fence_after();
+            #pragma unroll
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
+            {
+                const int t = 4 * tt + h;
+                uint32_t o[8];
+                if (p.knob & 1)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = w[tt][j % (K + 1)];
+                }
+                else if (q & 1) decode16<K, cb, 1>(w[tt], o); else decode16<K, cb, 0>(w[tt], o);
+                if (!(p.knob & 2))
+                    tmem_st_32x32b_x8(tmem_base + lane_base + a_cols0 + as * TC_A_STAGE_COLS + 8 * t, o);
+                else if (o[0] == 0x12345678u && o[7] == 0x9abcdef0u) p.counters[0] = 1;     // keep the values alive
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
+            if (warp == TC_DEC_WARP0 && lane == 0) { if (u == 0) stamp(4); if (u == n_units - 1) stamp(10); }
+            if (++s == S) { s = 0; sph ^= 1; }
+            if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
     }
     else if (warp >= TC_EPI_WARP0)
@@ -305,7 +355,6 @@ gemm_tc_kernel(const TcParams p)
         const int col = strip_col(q, lane);
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
         float* tile = reinterpret_cast<float*>(smem + L.off_tile);
-        const size_t esz = p.c_fp32 ? 4 : 2;
         auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
         const int part_stride = p.NT * 128;
 
@@ -333,8 +382,9 @@ gemm_tc_kernel(const TcParams p)
             const bool full = n_contrib == 1;
             float* my_part = p.ws + (size_t) (2 * blockIdx.x + (ubeg >= gs ? 0 : 1)) * part_stride;
 
-            mbar_wait(D_FULL(dbuf), dphase);
+            mbar_wait<512>(D_FULL(dbuf), dphase);
             tc_fence_after();
+            if (u == 0 && et == 0) stamp(7);
             const uint32_t d_addr = tmem_base + lane_base + d_cols0 + dbuf * p.NT;
             for (int c0 = 0; c0 < p.m; c0 += 16)
             {
@@ -396,11 +446,13 @@ gemm_tc_kernel(const TcParams p)
             }
             u += seg;
         }
+        if (et == 0) stamp(8);
     }
 
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(9);
     if (warp == 1)
     {
         tc_fence_after();
@@ -410,14 +462,56 @@ gemm_tc_kernel(const TcParams p)
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 
+// ---- tensor map for the trellis: 2-D view [k/16 rows][n/16 * 32K bytes] in uint64 elements, box = 8 rows x 256K bytes ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out)
+{
+    static PFN_encodeTiled encode = nullptr;
+    static std::mutex mu;
+    struct Key { const void* p; int k, n, K; bool operator==(const Key& o) const { return p == o.p && k == o.k && n == o.n && K == o.K; } };
+    struct Hash { size_t operator()(const Key& x) const { return std::hash<const void*>()(x.p) ^ ((size_t) x.k * 1315423911u) ^ ((size_t) x.n << 20) ^ (size_t) x.K; } };
+    static std::unordered_map<Key, CUtensorMap, Hash> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode)
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        EXL3B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        EXL3B_CHECK(fn && qres == cudaDriverEntryPointSuccess, EXL3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        encode = (PFN_encodeTiled) fn;
+    }
+    Key key{B, k, n, K};
+    auto it = cache.find(key);
+    if (it == cache.end())
+    {
+        CUtensorMap tm;
+        const cuuint64_t row_bytes = (cuuint64_t) (n / 16) * 32 * K;
+        cuuint64_t gdim[2] = { row_bytes / 8, (cuuint64_t) (k / 16) };
+        cuuint64_t gstride[1] = { row_bytes };
+        cuuint32_t box[2] = { (cuuint32_t) (32 * K), 8 };
+        cuuint32_t estr[2] = { 1, 1 };
+        CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(B), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        EXL3B_CHECK(r == CUDA_SUCCESS, EXL3B_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for trellis %p k=%d n=%d K=%d", (int) r, B, k, n, K);
+        if (cache.size() > 65536) cache.clear();
+        it = cache.emplace(key, tm).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 template <int K, int cb>
-static cudaError_t tc_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p)
+static cudaError_t tc_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap)
 {
     static bool attr_set[32] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (!attr_set[dev & 31])
     {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<K, cb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<K, cb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 31] = true;
     }
@@ -427,14 +521,20 @@ static cudaError_t tc_launch(cudaStream_t stream, int grid, int smem_bytes, cons
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<K, cb>, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<K, cb>, p, tmap);
 }
 
 template <int K, int cb>
-static void tc_launch_v(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, cudaError_t* err)
+static void tc_launch_v(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap,
+                        cudaError_t* err)
 {
-    *err = tc_launch<K, cb>(stream, grid, smem_bytes, p);
+    *err = tc_launch<K, cb>(stream, grid, smem_bytes, p, tmap);
 }
+
+unsigned long long* g_tc_dbg = nullptr;
+int g_tc_knob = 0;
+void tc_set_debug_buffer(unsigned long long* d) { g_tc_dbg = d; }
+void tc_set_knob(int k) { g_tc_knob = k; }
 
 bool gemm_tc_supported(const GemmArgs& a)
 {
@@ -460,15 +560,22 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
 int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 {
     const size_t esz = a.c_fp32 ? 4 : 2;
+    CUtensorMap tmap;
+    { int r = get_weight_tmap(a.B, a.k, a.n, a.K, &tmap); if (r) return r; }
     for (int m0 = 0; m0 < a.m; m0 += 256)
     {
         const int m = a.m - m0 < 256 ? a.m - m0 : 256;
         const int NT = (m + 15) / 16 * 16;
         const int slot = ctx->next_slot();
-        const size_t xh_bytes = (size_t) (a.k / 128) * NT * 256;
-        int r = ensure_xh_tiled(ctx, xh_bytes); if (r) return r;
-        uint8_t* xh_tiled = ctx->xh_tiled + (size_t) (slot % DevCtx::XH_SLOTS) * ctx->xh_tiled_slot_bytes;
-        r = launch_had_tiled(stream, a.A + (size_t) m0 * a.k, xh_tiled, a.suh, m, a.k, NT); if (r) return r;
+        const bool fused_x = m <= 8;
+        uint8_t* xh_tiled = nullptr;
+        if (!fused_x)
+        {
+            const size_t xh_bytes = (size_t) (a.k / 128) * NT * 256;
+            int r = ensure_xh_tiled(ctx, xh_bytes); if (r) return r;
+            xh_tiled = ctx->xh_tiled + (size_t) (slot % DevCtx::XH_SLOTS) * ctx->xh_tiled_slot_bytes;
+            r = launch_had_tiled(stream, a.A + (size_t) m0 * a.k, xh_tiled, a.suh, m, a.k, NT); if (r) return r;
+        }
 
         TcParams p{};
         p.xh_tiled = xh_tiled; p.B = a.B; p.C = (char*) a.C + (size_t) m0 * a.n * esz; p.svh = a.svh;
@@ -479,14 +586,20 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         p.a_stages = small ? 3 : 4;
         p.d_bufs = NT <= 128 ? 2 : 1;
         p.b_load_bytes = m <= 8 ? 2048 : NT * 256;
-        const int stage_bytes = 2048 * a.K + NT * 256;
-        const int budget = small ? 96 * 1024 : 180 * 1024;
+        const int b_bytes = fused_x ? 2048 : NT * 256;       // m <= 8: only the first row group is ever written / needed
+        const int stage_bytes = 2048 * a.K + b_bytes;
+        const int budget = 200 * 1024;
         int stages = budget / stage_bytes;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         if (stages < 2) stages = 2;
         p.stages = stages;
-        const TcSmemLayout L = tc_smem_layout(a.K, NT, stages);
-        EXL3B_CHECK(L.total <= 200 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: shared-memory budget exceeded");
+        p.dbg = g_tc_dbg;
+        p.knob = g_tc_knob;
+        p.A_raw = fused_x ? a.A + (size_t) m0 * a.k : nullptr;
+        p.suh = a.suh;
+        p.b_bytes = b_bytes;
+        const TcSmemLayout L = tc_smem_layout(a.K, b_bytes, stages);
+        EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: shared-memory budget exceeded");
 
         const long long U = (long long) (a.k / 128) * (a.n / 128);
         int grid = ctx->num_sms;
@@ -497,7 +610,7 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
 
         cudaError_t err = cudaSuccess;
-        EXL3B_DISPATCH_K_CB(tc_launch_v, a.K, a.cb, stream, grid, L.total, p, &err);
+        EXL3B_DISPATCH_K_CB(tc_launch_v, a.K, a.cb, stream, grid, L.total, p, tmap, &err);
         count_launch();
         EXL3B_CUDA(err);
     }

@@ -1,0 +1,520 @@
+// tcgen05 kind::i8 EXL3 decode-GEMM for the mul1 codebook, m <= 4 ("TC-i8 path", tag 210).
+//
+// Why: the bit-exact mul1 decode needs IMAD + IDP.4A per weight on the same issue pipe plus pack + HFMA2; measured
+// (profiles/r01_microbench_pipes.log) that caps the decode at ~20 weights/clk/SM = ~45 % of the HBM rate at K = 4.
+// The mul1 value is AFFINE in the byte sum of x = state * 0x83DCD12D:
+//        w = k_inv * (1024 + b0 + b1 + b2 + b3) + k_bias              (codebook.cuh:77-89, before its fp16 rounding)
+// so   sum_k a_k w_kn = k_inv * sum_k a_k (b0+b1+b2+b3)_kn + (1024 k_inv + k_bias) * sum_k a_k.
+// The first sum is an integer GEMM whose K-elements are the four product BYTES: the decode thread stores the raw
+// 32-bit product into a TMEM kind::i8 A operand (4 u8 along K) and the tensor core sums the bytes while contracting
+// with the activation, which is quantised per row to a balanced pair of signed 8-bit digits (q = 256 hi + lo,
+// |q| <= 32512, i.e. 16-bit activations; hi and lo are two N-columns, each digit replicated over the 4 bytes).
+// Per weight that leaves window extraction + ONE IMAD (measured mix: 42.7 weights/clk/SM).
+//
+// Numerics: integer accumulation is exact; what differs from the reference's fp16 kernel is (a) the per-weight fp16
+// rounding of the codebook value is skipped (rel-RMS ~3e-4 of the output, unbiased) and (b) activations carry
+// 16-bit instead of fp16 quantisation noise (smaller).  The reference's own default decode path for mul1 at m <= 2 is
+// its int8-activation GEMV with ~0.9 % output RMS deviation (exl3_gemv_int8.cu:19-20); this path is ~30x closer to
+// the fp16 kernel than that.  Tolerances are asserted in tests/test_gpu_parity.py::test_gemm_i8_*.
+//
+// Structure is the same as gemm_tc.cu (stream-K units of 128x128 weights, TMA ring, TMEM operand stages, warp roles);
+// differences: A stage = 128 TMEM columns (one 32-bit product per weight), 16 MMAs (K = 32 bytes = 8 weights) per
+// unit, a CTA prologue that finds the per-row |xh| maximum (all 18 non-issuer warps, redundantly per CTA: m <= 4),
+// per-unit activation digits + digit sums written by the transform warps, int32 accumulators.
+#include "tc_common.cuh"
+
+namespace exl3b {
+
+using namespace ptx;
+
+constexpr int I8_MAX_M = 4;
+constexpr int I8_A_STAGE_COLS = 128;
+constexpr int I8_A_STAGES = 3;
+constexpr int I8_D_COL0 = I8_A_STAGES * I8_A_STAGE_COLS;      // 384
+constexpr int I8_NT = 16;                                      // N: rows 2r = hi digit, 2r+1 = lo digit of row r
+constexpr int I8_B_BYTES = 4096;                               // one row group: 32 K-chunks x (8 rows x 16 B)
+constexpr int I8_B_STAGE = I8_B_BYTES + 64;                    // + per-row digit sums of the unit
+constexpr int I8_SUB_UNITS = 96;                               // int32 accumulator safety: <= 12288 k per accumulation
+constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 256 + 0  -> hi in [-127, 127]
+
+__host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int stages)
+{
+    return tc_smem_layout(K, I8_B_STAGE, stages);
+}
+
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const TcSmemLayout L = i8_smem_layout(K, p.stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    const uint32_t bar0 = smem_u32(bars);
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto X_FULL = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (3 * S + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 4 + s); };
+    auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
+    auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [I8_MAX_M] float bits, >= 0
+    int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                            // [2][I8_MAX_M] digit sums per D buffer
+
+    pdl_launch_dependents();
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
+        for (int r = 0; r < I8_MAX_M; ++r) s_absmax[r] = 0u;
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int KB = p.k / 128;
+    const int strips = p.n / 128;
+    const long long U = (long long) KB * strips;
+    const int G = gridDim.x;
+    const long long ubeg = unit_begin(U, G, blockIdx.x), uend = unit_begin(U, G, blockIdx.x + 1);
+    const int n_units = (int) (uend - ubeg);
+
+    // fp16 transformed activation of (row r, k-block kb), 4 values per lane, exactly as the reference's A_had
+    auto xh_block = [&](int r, int kb, float (&v)[4])
+    {
+        uint2 raw = *reinterpret_cast<const uint2*>(p.A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
+        half2 a = *reinterpret_cast<half2*>(&raw.x), b = *reinterpret_cast<half2*>(&raw.y);
+        if (p.suh)
+        {
+            const uint2 scb = *reinterpret_cast<const uint2*>(p.suh + kb * 128 + lane * 4);
+            a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
+            b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
+            float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
+            had128_warp(v0, v1, v2, v3, lane);
+            a = __floats2half2_rn(v0 * R_SCALE, v1 * R_SCALE);
+            b = __floats2half2_rn(v2 * R_SCALE, v3 * R_SCALE);
+        }
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    };
+
+    // ---- prologue: per-row max |xh| over the whole row (warps 2..19), overlapped with the first weight loads ----
+    if (warp == 0)
+    {
+        // producer starts streaming weights immediately (below); it does not take part in the prologue
+    }
+    if (warp >= TC_XF_WARP0 && warp < TC_EPI_WARP0)
+    {
+        pdl_wait();                                       // A is produced by the previous kernel
+        const int nw = TC_EPI_WARP0 - TC_XF_WARP0;       // 18 warps
+        for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
+        {
+            const int r = task / KB, kb = task % KB;
+            float v[4];
+            xh_block(r, kb, v);
+            float mx = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) atomicMax(&s_absmax[r], __float_as_uint(mx));
+        }
+        asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
+    }
+
+    if (warp == 0)
+    {
+        // =========================== producer ===========================
+        if (elect_one()) prefetch_tmap(&tmap_w);
+        const uint64_t pol_w = policy_evict_first();
+        const uint32_t w_smem0 = smem_u32(smem);
+        int strip = (int) (ubeg / KB), kb = (int) (ubeg % KB);
+        int s = 0, ph = 0;
+        for (int u = 0; u < n_units; ++u)
+        {
+            if (u >= S) mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+            if (elect_one())
+            {
+                mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
+                tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
+            }
+            if (++kb == KB) { kb = 0; ++strip; }
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        __syncwarp();
+    }
+    else if (warp == 1)
+    {
+        // =========================== MMA issuer ===========================
+        const uint32_t idesc = idesc_u8s8_s32(128, I8_NT);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t x_smem0 = smem_u32(smem + L.off_b);
+        const uint64_t desc_hi = smem_desc(0, 128, 4096, 0);       // K-adjacent core matrices 128 B apart, row groups 4096 B
+        int dbuf = 0, dphase = 0, seg_left = 0, sub_left = 0;
+        uint32_t acc = 0;
+        int tsum = 0;                                              // lane r < m: digit sum of row r over the sub-segment
+        int kb = (int) (ubeg % KB);
+        int s = 0, sph = 0, as = 0, aph = 0;
+        for (int u = 0; u < n_units; ++u)
+        {
+            if (seg_left == 0)
+            {
+                const int to_strip_end = KB - kb;
+                seg_left = (n_units - u) < to_strip_end ? (n_units - u) : to_strip_end;
+            }
+            if (sub_left == 0)
+            {
+                sub_left = seg_left < I8_SUB_UNITS ? seg_left : I8_SUB_UNITS;
+                mbar_wait(D_EMPTY(dbuf), dphase ^ 1);
+                acc = 0;
+                tsum = 0;
+            }
+            mbar_wait(X_FULL(s), sph);
+            mbar_wait(A_FULL(as), aph);
+            tc_fence_after();
+            if (lane < p.m) tsum += *reinterpret_cast<const int*>(smem + L.off_b + s * L.b_bytes + I8_B_BYTES + 4 * lane);
+            const uint32_t d_addr = tb + I8_D_COL0 + dbuf * I8_NT;
+            const uint32_t a_addr = tb + as * I8_A_STAGE_COLS;
+            const uint32_t b_addr = x_smem0 + s * L.b_bytes;
+            --seg_left; --sub_left;
+            if (sub_left == 0)
+            {
+                if (lane < p.m) s_tout[dbuf * I8_MAX_M + lane] = tsum;      // visible to the epilogue before D_FULL fires
+                __threadfence_block();
+                __syncwarp();
+            }
+            if (elect_one())
+            {
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    mma_i8_ts(d_addr, a_addr + 8 * j, desc_hi | (uint64_t) (((b_addr + j * 256) >> 4) & 0x3fff), idesc, acc);
+                    acc = 1;
+                }
+                tc_commit(A_EMPTY(as));
+                tc_commit(W_EMPTY(s));
+                if (sub_left == 0) tc_commit(D_FULL(dbuf));
+            }
+            acc = 1;
+            __syncwarp();
+            if (sub_left == 0) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
+            if (++kb == KB) kb = 0;
+            if (++s == S) { s = 0; sph ^= 1; }
+            if (++as == I8_A_STAGES) { as = 0; aph ^= 1; }
+        }
+        __syncwarp();
+    }
+    else if (warp < TC_DEC_WARP0)
+    {
+        // =========================== activation digits (per unit) ===========================
+        const int xw = warp - TC_XF_WARP0;
+        float inv_scale[I8_MAX_M];
+        #pragma unroll
+        for (int r = 0; r < I8_MAX_M; ++r)
+        {
+            const float mx = __uint_as_float(s_absmax[r]);
+            inv_scale[r] = mx > 0.f ? (float) I8_QMAX / mx : 0.f;
+        }
+        int kb = (int) ((ubeg + xw) % KB);
+        int s = xw % S, ph = 0;
+        const int kstep = 2 % KB;
+        for (int u = xw; u < n_units; u += 2)
+        {
+            mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+            uint8_t* dst = smem + L.off_b + s * L.b_bytes;
+            #pragma unroll
+            for (int r = 0; r < I8_MAX_M; ++r)
+            {
+                if (r < p.m)
+                {
+                    float v[4];
+                    xh_block(r, kb, v);
+                    uint32_t hi_w[4], lo_w[4];
+                    int qs = 0;
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                    {
+                        const int q = __float2int_rn(v[e] * inv_scale[r]);
+                        const int hi = (q + 128) >> 8;
+                        const int lo = q - (hi << 8);
+                        qs += q;
+                        hi_w[e] = (uint32_t) (hi & 0xff) * 0x01010101u;          // digit replicated over the 4 product bytes
+                        lo_w[e] = (uint32_t) (lo & 0xff) * 0x01010101u;
+                    }
+                    // chunk = lane (4 k-values x 4 bytes = 16 B), rows 2r (hi) and 2r+1 (lo) of row group 0
+                    *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r) * 16) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+                    *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r + 1) * 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                    if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(X_FULL(s));
+            kb += kstep; if (kb >= KB) kb -= KB;
+            s += 2; if (s >= S) { s -= S; ph ^= 1; }
+        }
+    }
+    else if (warp < TC_EPI_WARP0)
+    {
+        // =========================== decode ===========================
+        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;
+        const int tl = strip_tile(q, lane), chunk = lane & 7;
+        const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        int s = 0, sph = 0, as = 0, aph = 0;
+        for (int u = 0; u < n_units; ++u)
+        {
+            mbar_wait(W_FULL(s), sph);
+            const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
+            uint32_t w[TC_DEC_TILES][K + 1];
+            #pragma unroll
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
+            {
+                const int t = 4 * tt + h;
+                const uint32_t* cp = wst + (t * 8 + tl) * (8 * K) + chunk * K;
+                if constexpr (K % 4 == 0)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; j += 4)
+                    {
+                        uint4 v = *reinterpret_cast<const uint4*>(cp + j);
+                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y; w[tt][3 + j] = v.z; w[tt][4 + j] = v.w;
+                    }
+                }
+                else if constexpr (K % 2 == 0)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; j += 2)
+                    {
+                        uint2 v = *reinterpret_cast<const uint2*>(cp + j);
+                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y;
+                    }
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int j = 0; j < K; ++j) w[tt][1 + j] = cp[j];
+                }
+            }
+            #pragma unroll
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
+                w[tt][0] = __shfl_sync(0xffffffffu, w[tt][K], prev_lane);
+            mbar_wait(A_EMPTY(as), aph ^ 1);
+            tc_fence_after();
+            #pragma unroll
+            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
+            {
+                const int t = 4 * tt + h;
+                uint32_t o[16];
+                if (q & 1) decode16_i8<K, 1>(w[tt], o); else decode16_i8<K, 0>(w[tt], o);
+                tmem_st_32x32b_x16(tmem_base + lane_base + as * I8_A_STAGE_COLS + 16 * t, o);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
+            if (++s == S) { s = 0; sph ^= 1; }
+            if (++as == I8_A_STAGES) { as = 0; aph ^= 1; }
+        }
+    }
+    else
+    {
+        // =========================== epilogue ===========================
+        pdl_wait();
+        const int q = warp & 3;
+        const int et = threadIdx.x - TC_EPI_WARP0 * 32;
+        const int col = strip_col(q, lane);
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        float* tile = reinterpret_cast<float*>(smem + L.off_tile);
+        auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+        const int part_stride = I8_MAX_M * 128;
+
+        // the prologue result is needed here too: wait for it through the first D_FULL (the MMA warp only gets
+        // operands after the transform warps passed the prologue barrier), then read the maxima
+        const float k_inv = __half2float(__ushort_as_half((unsigned short) 0x1eee));
+        const float k_bias = __half2float(__ushort_as_half((unsigned short) 0xc931));
+        const float c1 = 1534.0f * k_inv + k_bias;        // (1024 + 510) k_inv + k_bias: residue of the fp16-rounded bias
+
+        auto emit_rows = [&](int strip)
+        {
+            epi_bar();
+            if (q < p.m)
+                output_row_128(tile + q * 128, (char*) p.C, (size_t) q * p.n + strip * 128,
+                               p.svh ? p.svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
+            epi_bar();
+        };
+
+        int dbuf = 0, dphase = 0;
+        int u = 0;
+        while (u < n_units)
+        {
+            const long long g = ubeg + u;
+            const int strip = (int) (g / KB), kb = (int) (g % KB);
+            const int to_strip_end = KB - kb;
+            const int seg = (n_units - u) < to_strip_end ? (n_units - u) : to_strip_end;
+            const long long gs = (long long) strip * KB;
+            const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + KB - 1);
+            const int n_contrib = c_b - c_a + 1;
+            const bool full = n_contrib == 1;
+            float* my_part = p.ws + (size_t) (2 * blockIdx.x + (ubeg >= gs ? 0 : 1)) * part_stride;
+
+            float facc[I8_MAX_M];
+            #pragma unroll
+            for (int r = 0; r < I8_MAX_M; ++r) facc[r] = 0.f;
+            for (int done = 0; done < seg; )
+            {
+                const int sub = (seg - done) < I8_SUB_UNITS ? (seg - done) : I8_SUB_UNITS;
+                mbar_wait<512>(D_FULL(dbuf), dphase);
+                tc_fence_after();
+                uint32_t rr[16];
+                tmem_ld_32x32b_x16(tmem_base + lane_base + I8_D_COL0 + dbuf * I8_NT, rr);
+                tc_wait_ld();
+                #pragma unroll
+                for (int r = 0; r < I8_MAX_M; ++r)
+                {
+                    if (r < p.m)
+                    {
+                        const int T = s_tout[dbuf * I8_MAX_M + r];
+                        // sum_k q_k (bytesum_kn - 510), exact in 64-bit
+                        const long long sp = 256ll * (int) rr[2 * r] + (long long) (int) rr[2 * r + 1] - 510ll * T;
+                        const float mx = __uint_as_float(s_absmax[r]);
+                        const float scale = mx / (float) I8_QMAX;
+                        facc[r] += scale * (k_inv * (float) sp + c1 * (float) T);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(D_EMPTY(dbuf));
+                dbuf ^= 1; if (dbuf == 0) dphase ^= 1;
+                done += sub;
+            }
+
+            if (full)
+            {
+                #pragma unroll
+                for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) tile[r * 128 + col] = facc[r];
+                emit_rows(strip);
+            }
+            else
+            {
+                #pragma unroll
+                for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) my_part[r * 128 + col] = facc[r];
+                __threadfence();
+                epi_bar();
+                if (et == 0)
+                {
+                    const int old = atomicAdd(&p.counters[strip], 1);
+                    const int last = old == n_contrib - 1;
+                    if (last) p.counters[strip] = 0;
+                    *s_flag = last;
+                }
+                epi_bar();
+                if (*s_flag)
+                {
+                    __threadfence();
+                    #pragma unroll
+                    for (int r = 0; r < I8_MAX_M; ++r)
+                    {
+                        if (r < p.m)
+                        {
+                            float a = 0.f;
+                            for (int c = c_a; c <= c_b; ++c)                 // fixed order: deterministic
+                            {
+                                const float* part = p.ws + (size_t) (2 * c + (unit_begin(U, G, c) >= gs ? 0 : 1)) * part_stride;
+                                a += __ldcg(part + r * 128 + col);
+                            }
+                            tile[r * 128 + col] = a;
+                        }
+                    }
+                    emit_rows(strip);
+                }
+                epi_bar();
+            }
+            u += seg;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+    {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+
+template <int K>
+static cudaError_t i8_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap)
+{
+    static bool attr_set[32] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_set[dev & 31])
+    {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_i8_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 31] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_i8_kernel<K>, p, tmap);
+}
+
+bool gemm_tc_i8_supported(const GemmArgs& a)
+{
+    return a.cb == 2 && a.m >= 1 && a.m <= I8_MAX_M && a.k >= 128 && a.n >= 128 && a.k % 128 == 0 && a.n % 128 == 0;
+}
+
+int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
+{
+    CUtensorMap tmap;
+    { int r = get_weight_tmap(a.B, a.k, a.n, a.K, &tmap); if (r) return r; }
+    const int slot = ctx->next_slot();
+    TcParams p{};
+    p.B = a.B; p.C = a.C; p.svh = a.svh; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
+    p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
+    p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob = g_tc_knob;
+    const int stage_bytes = 2048 * a.K + I8_B_STAGE;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) stages = 2;
+    p.stages = stages; p.b_bytes = I8_B_STAGE;
+    const TcSmemLayout L = i8_smem_layout(a.K, stages);
+    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): shared-memory budget exceeded");
+    const long long U = (long long) (a.k / 128) * (a.n / 128);
+    int grid = ctx->num_sms;
+    if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
+    if (grid > U) grid = (int) U;
+    EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+    cudaError_t err = cudaSuccess;
+    switch (a.K)
+    {
+        case 1: err = i8_launch<1>(stream, grid, L.total, p, tmap); break;
+        case 2: err = i8_launch<2>(stream, grid, L.total, p, tmap); break;
+        case 3: err = i8_launch<3>(stream, grid, L.total, p, tmap); break;
+        case 4: err = i8_launch<4>(stream, grid, L.total, p, tmap); break;
+        case 5: err = i8_launch<5>(stream, grid, L.total, p, tmap); break;
+        case 6: err = i8_launch<6>(stream, grid, L.total, p, tmap); break;
+        case 7: err = i8_launch<7>(stream, grid, L.total, p, tmap); break;
+        case 8: err = i8_launch<8>(stream, grid, L.total, p, tmap); break;
+    }
+    count_launch();
+    EXL3B_CUDA(err);
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return EXL3B_TAG_TC_I8;
+}
+
+}  // namespace exl3b

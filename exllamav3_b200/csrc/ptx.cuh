@@ -8,6 +8,16 @@ namespace exl3b { namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
+// One elected lane of a fully converged warp.  Keeping the surrounding control flow warp-uniform lets ptxas keep TMA /
+// tcgen05 operands in uniform registers; issuing from inside an `if (lane == 0)` region instead costs a
+// R2UR "waterfall" loop of ~16 dependent instructions per UTCHMMA (measured: 56 cycles per MMA issue).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -29,23 +39,44 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of polling -- polling warps (epilogue / MMA / producer roles) were measured to consume ~40 % of all issue
+// slots of the first version of the kernel (profiles/r01_ncu_tc_v1_notes.md).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall-clock
+// (%globaltimer, checked every 1024 polls), not an iteration count: try_wait returns early whenever ANY barrier
+// activity wakes the warp, so iteration counts say nothing about elapsed time.
+// SLEEP_NS > 0 adds an explicit back-off for roles whose waits are long and not latency critical (epilogue waiting
+// for a whole segment, producer waiting for a free ring slot): polling warps otherwise burn issue slots the decode
+// warps need (measured: ~12 % of all issued instructions came from four epilogue warps polling every ~30 ns).
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity))
     {
-        if (++spins > (1u << 26)) { printf("exl3b: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
-                                           blockIdx.x, threadIdx.x, bar, parity); __trap(); }
+        if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if ((++polls & 1023u) == 0)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull)
+            {
+                printf("exl3b: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
     }
 }
 
@@ -66,6 +97,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
+// 2-D tiled TMA copy (SASS UTMALDG): box at element coordinates (c0 = innermost, c1 = row) of a CUtensorMap
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%2, %3}], [%4], %5;"
+                 :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }
 
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
@@ -112,6 +155,21 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::i8 (8-bit integers -> int32), one CTA
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -145,6 +203,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __host__ __forceinline__ uint32_t idesc_f16_f32(int M, int N, bool b_mn_major = false)
 {
     return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
+// kind::i8: A unsigned 8-bit (format 0), B signed 8-bit (format 1), int32 accumulate (c_format 2), both K-major
+__device__ __host__ __forceinline__ uint32_t idesc_u8s8_s32(int M, int N)
+{
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
 }}  // namespace exl3b::ptx

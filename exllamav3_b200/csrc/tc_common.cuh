@@ -1,0 +1,69 @@
+// Shared declarations of the tcgen05 kernels (exact fp16 path: gemm_tc.cu, int8 codebook path: gemm_tc_i8.cu).
+#pragma once
+#include "common.cuh"
+#include "decode.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+
+namespace exl3b {
+
+constexpr int TC_THREADS = 768;
+constexpr int TC_XF_WARP0 = 2;               // warps 2,3: in-kernel input transform (small m)
+constexpr int TC_DEC_WARP0 = 4;
+constexpr int TC_DEC_WARPS = 16;             // 4 per lane quarter: tiles {h, h+4} of every unit
+constexpr int TC_DEC_TILES = 8 * 4 / TC_DEC_WARPS;
+constexpr int TC_EPI_WARP0 = TC_DEC_WARP0 + TC_DEC_WARPS;
+constexpr int TC_MAX_STAGES = 16;
+constexpr int TC_A_STAGE_COLS = 64;          // 128 k-values x fp16, 2 per 32-bit TMEM column
+
+struct TcParams
+{
+    const uint8_t* xh_tiled;     // [k/128][NT/8][16][8][8] fp16 (core-matrix tiles)
+    const uint32_t* B;
+    void* C;
+    const half* svh;
+    int m, k, n, NT;
+    int c_fp32;
+    float out_scale;
+    float* ws;
+    int* counters;
+    int stages;                  // smem ring depth
+    int b_bytes;                 // bytes reserved per activation stage
+    int b_load_bytes;            // bytes of the activation tile copied per unit
+    int a_stages;                // TMEM A-operand stages (3 or 4)
+    int d_bufs;                  // TMEM accumulator buffers (1 or 2)
+    int tmem_cols;               // 256 or 512
+    const half* A_raw;           // fused input transform (m <= 8): raw activations (m, k) and suh; null -> xh_tiled is used
+    const half* suh;
+    int knob;                    // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA
+    unsigned long long* dbg;     // optional per-CTA timeline (16 x u64 per CTA), bring-up only
+};
+
+struct TcSmemLayout
+{
+    int w_bytes, b_bytes, off_b, off_tile, off_bars, total;
+};
+
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int K, int b_bytes, int stages)
+{
+    TcSmemLayout L;
+    L.w_bytes = 2048 * K;
+    L.b_bytes = b_bytes;
+    L.off_b = stages * L.w_bytes;
+    L.off_tile = L.off_b + stages * L.b_bytes;
+    L.off_bars = L.off_tile + 16 * 128 * 4;
+    L.total = L.off_bars + 1024;
+    return L;
+}
+
+// ---- work partition helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
+__device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
+
+
+int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out);
+extern unsigned long long* g_tc_dbg;
+extern int g_tc_knob;
+
+}  // namespace exl3b

@@ -54,6 +54,7 @@ assert _lib.exl3b_abi_version() == 1
 
 EXL3B_TAG_SIMT = 100
 EXL3B_TAG_TC = 200
+EXL3B_TAG_TC_I8 = 210
 
 lib = _lib      # raw handle for bench.py / tests (symbol export checks)
 lib_path = _LIB_PATH

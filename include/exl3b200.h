@@ -44,7 +44,8 @@ enum exl3b_status
 /* Kernel-path tags returned by exl3b_gemm / exl3b_mgemm */
 #define EXL3B_TAG_NOP 0        /* empty problem                                            */
 #define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
-#define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM                               */
+#define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
+#define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path (mul1, m <= 4)            */
 
 int exl3b_abi_version(void);
 
@@ -56,7 +57,7 @@ const char* exl3b_last_error(void);
 int exl3b_num_sms(int device);
 int exl3b_cc(int device);
 
-/* Force a kernel path for exl3b_gemm on this process: 0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC.
+/* Force a kernel path for exl3b_gemm on this process: 0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC, EXL3B_TAG_TC_I8.
    (The reference exposes force_shape_idx / force_num_sms per call for the same purpose.) Returns previous value. */
 int exl3b_set_gemm_path(int tag);
 

@@ -276,13 +276,57 @@ def test_mgemm_modes(cuda):
             assert rel_err(C[0].cpu().numpy(), golden[f"mgemm_d_{int(fp32)}"])[0] <= 5e-3
 
 
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("m", [1, 2, 4])
+def test_gemm_i8_tensor_core_path(cuda, K, m):
+    """
+    mul1 int8 tensor-core codebook path (tag 210, default for mul1 at m <= 4).  Two bars:
+      * implementation: agrees with the exact integer model of the path (oracle.exl3_gemm_i8_model) to fp32 round-off
+      * approximation: distance to the fp64 oracle of the reference math  max-abs <= 2e-3 max|y|, rel-RMS <= 1e-3
+        (the skipped per-weight fp16 rounding; the reference's own default int8 GEMV deviates ~9e-3, exl3_gemv_int8.cu:19-20)
+    """
+    from exllamav3_b200 import ext
+    prev = ext.set_gemm_path(ext.EXL3B_TAG_TC_I8)
+    try:
+        for (k, n) in ((512, 384), (2048, 128), (128, 1024)):
+            tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+            model = orc.exl3_gemm_i8_model(x, tr, suh, svh, K)
+            ref = orc.exl3_gemm_f64(x, tr, suh, svh, K, 2)
+            for fp32 in (True, False):
+                y, _, tag = run_gemm(ext, cuda, x, tr, suh, svh, K, 2, fp32)
+                assert tag == ext.EXL3B_TAG_TC_I8
+                mx, rms = rel_err(y, model)
+                assert mx <= (2e-5 if fp32 else 1.5e-3) and rms <= (1e-5 if fp32 else 5e-4), (K, m, k, n, fp32, mx, rms)
+                mx, rms = rel_err(y, ref)
+                assert mx <= 2e-3 + (2.0 ** -10 if not fp32 else 0) and rms <= 1e-3, (K, m, k, n, fp32, mx, rms)
+        # zero rows and huge dynamic range do not break the per-row activation scale
+        tr, suh, svh, x = orc.make_synthetic(512, 256, 4, m=3)
+        x[1] = 0
+        x[2] *= np.float16(100.0)
+        y, _, _ = run_gemm(ext, cuda, x, tr, suh, svh, 4, 2, True)
+        ref = orc.exl3_gemm_f64(x, tr, suh, svh, 4, 2)
+        assert float(np.abs(y[1]).max()) == 0.0
+        for r in (0, 2):
+            assert rel_err(y[r:r + 1], ref[r:r + 1])[0] <= 2e-3
+        # forcing the path outside its domain (m > 4) is an error, not a silent fallback
+        with pytest.raises(RuntimeError, match="int8 tensor-core path forced"):
+            ext.exl3_gemm(T(np.zeros((5, 512), np.float16), cuda), T(tr, cuda),
+                          torch.empty((5, 256), dtype=torch.half, device=cuda), T(suh, cuda), None, T(svh, cuda),
+                          -1, False, True, 0)
+    finally:
+        ext.set_gemm_path(prev)
+
+
 def test_tc_determinism_and_stream_k(cuda):
     """Split-K partials are combined in a fixed order: repeated launches are bit-identical; shapes chosen so that
     strips are split across CTAs (k large, n small) and so that CTAs span several strips (n large)."""
     from exllamav3_b200 import ext
-    prev = ext.set_gemm_path(ext.EXL3B_TAG_TC)
+    prev = ext.set_gemm_path(0)
     try:
-        for (k, n, m) in ((8192, 128, 1), (4096, 256, 3), (128, 8192, 2), (1024, 2048, 16)):
+        for (k, n, m, path) in ((8192, 128, 1, ext.EXL3B_TAG_TC), (4096, 256, 3, ext.EXL3B_TAG_TC), (128, 8192, 2, ext.EXL3B_TAG_TC),
+                                (1024, 2048, 16, ext.EXL3B_TAG_TC), (16384, 128, 1, ext.EXL3B_TAG_TC_I8),
+                                (4096, 256, 3, ext.EXL3B_TAG_TC_I8), (128, 8192, 2, ext.EXL3B_TAG_TC_I8)):
+            ext.set_gemm_path(path)
             tr, suh, svh, x = orc.make_synthetic(k, n, 4, m=m)
             ref = orc.exl3_gemm_f64(x, tr, suh, svh, 4, 2)
             outs = [run_gemm(ext, cuda, x, tr, suh, svh, 4, 2, True)[0] for _ in range(3)]

@@ -36,7 +36,7 @@ def run_case(name):
     if onehot is not None:
         x = np.zeros((m, k), np.float16); x[0, onehot] = 1.0
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    ext.set_gemm_path(ext.EXL3B_TAG_TC)
+    ext.set_gemm_path(int(os.environ.get("EXL3B_PATH", "200")))
     C = torch.full((m, n), float("nan"), dtype=torch.float if fp32 else torch.half, device=dev)
     A = T(x)
     tag = ext.exl3_gemm(A, T(tr), C, T(suh) if tr_on else None, torch.empty_like(A) if tr_on else None,
