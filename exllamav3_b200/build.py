@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexl3b200.so")
 
-SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "hgemm.cu"]
+SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "hgemm.cu", "hgemm_tc.cu"]
 HEADERS = ["common.cuh", "decode.cuh", "epilogue.cuh", "ptx.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "exl3b200.h")]
 
 NVCC_FLAGS = [
@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("EXL3B_TC_DEBUG", "0") != "0":       # bring-up build: in-kernel timeline stamps + experiment knobs
+    NVCC_FLAGS.append("-DEXL3B_TC_DEBUG")
 
 
 def _nvcc():

@@ -80,23 +80,32 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
     auto X_FULL = [&](int s) { return bar0 + 8u * (2 * S + s); };
     auto A_FULL = [&](int s) { return bar0 + 8u * (3 * S + s); };
-    auto A_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 4 + s); };
-    auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
-    auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
+    auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 16 + s); };
+    auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 18 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 20));
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
+#ifdef EXL3B_TC_DEBUG
+    const int KNOB = p.knob_;
+#else
+    constexpr int KNOB = 0;
+#endif
     auto stamp = [&](int slot)
     {
-        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[blockIdx.x * 16 + slot] = t; }
+#ifdef EXL3B_TC_DEBUG
+        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[blockIdx.x * 64 + slot] = t; }
+#else
+        (void) slot;
+#endif
     };
     if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / TC_DEC_GROUPS + 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS / TC_DEC_GROUPS); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
         fence_barrier_init();
     }
@@ -135,7 +144,8 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 {
                     mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
                     // one 2-D TMA box per unit: 8 tile-rows x (256*K bytes = 32*K uint64) of the trellis
-                    tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
+                    if (KNOB & 16) tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, 0, (strip * KB + kb) * 8, W_FULL(s), pol_w);
+                    else tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
                 }
             };
             auto issue_x = [&](int s, int kb)
@@ -162,7 +172,7 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             int s = (pre == S) ? 0 : pre, ph = (pre == S) ? 1 : 0;                   // ring position of unit `pre`
             for (int u = pre; u < n_units; ++u)
             {
-                mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+                mbar_wait<64>(W_EMPTY(s), ph ^ 1);
                 issue_w(s, strip, kb);
                 if (!fused_x) issue_x(s, kb);
                 next_unit();
@@ -205,7 +215,7 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 --seg_left;
                 if (elect_one())
                 {
-                    if (!(p.knob & 4))
+                    if (!(KNOB & 4))
                     {
                         #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -247,7 +257,7 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const int kstep = 2 % KB;
             for (int u = xw; u < n_units; u += 2)
             {
-                mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+                mbar_wait<64>(W_EMPTY(s), ph ^ 1);
                 uint8_t* dst = smem + L.off_b + s * L.b_bytes;
                 const uint2 scb = p.suh ? *reinterpret_cast<const uint2*>(p.suh + kb * 128 + lane * 4) : make_uint2(0, 0);
                 for (int r = 0; r < p.m; ++r)
@@ -277,73 +287,51 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     else if (warp >= TC_DEC_WARP0 && warp < TC_DEC_WARP0 + TC_DEC_WARPS)
     {
         // =========================== decode ===========================
-        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;              // h = 0..3
+        // Four groups of four warps (one warp per TMEM lane quarter); group g owns the units u = g (mod 4) and decodes
+        // ALL eight k-tiles of them, so the per-unit handshake cost (two mbarrier waits, shuffles, tcgen05.wait::st,
+        // two arrives: ~300 ns measured) is paid once per 8 tiles per warp and the groups run out of lockstep.
+        const int q = warp & 3, g = (warp - TC_DEC_WARP0) >> 2;
         const int tl = strip_tile(q, lane), chunk = lane & 7;
         const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
-        int s = 0, sph = 0, as = 0, aph = 0;
-        for (int u = 0; u < n_units; ++u)
+        int s = g % S, sph = (g / S) & 1, as = g % p.a_stages, aph = (g / p.a_stages) & 1;
+        const int s_step = TC_DEC_GROUPS % S, s_wrap = TC_DEC_GROUPS / S;                       // ring stride of a group
+        const int a_step = TC_DEC_GROUPS % p.a_stages, a_wrap = TC_DEC_GROUPS / p.a_stages;
+        for (int u = g; u < n_units; u += TC_DEC_GROUPS)
         {
-            mbar_wait(W_FULL(s), sph);
+            mbar_wait<32>(W_FULL(s), sph);
             if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
             const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
-            uint32_t w[TC_DEC_TILES][K + 1];
             #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)          // issue all shared-memory loads of this unit up front
+            for (int half = 0; half < 2; ++half)
             {
-                const int t = 4 * tt + h;
-                const uint32_t* cp = wst + (t * 8 + tl) * (8 * K) + chunk * K;
-                if constexpr (K % 4 == 0)
+                uint32_t w[4][K + 1];
+                tc_load_tiles4<K>(wst, tl, chunk, prev_lane, half * 4, 1, w);
+                if (half == 0) { mbar_wait(A_EMPTY(as), aph ^ 1); tc_fence_after(); }
+                #pragma unroll
+                for (int j = 0; j < 4; ++j)
                 {
-                    #pragma unroll
-                    for (int j = 0; j < K; j += 4)
+                    const int t = half * 4 + j;
+                    uint32_t o[8];
+                    if (KNOB & 1)
                     {
-                        uint4 v = *reinterpret_cast<const uint4*>(cp + j);
-                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y; w[tt][3 + j] = v.z; w[tt][4 + j] = v.w;
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = w[j][i % (K + 1)];
                     }
+                    else if (q & 1) decode16<K, cb, 1>(w[j], o); else decode16<K, cb, 0>(w[j], o);
+                    if (!(KNOB & 2))
+                        tmem_st_32x32b_x8(tmem_base + lane_base + a_cols0 + as * TC_A_STAGE_COLS + 8 * t, o);
+                    else if (o[0] == 0x12345678u && o[7] == 0x9abcdef0u) p.counters[0] = 1;     // keep the values alive
                 }
-                else if constexpr (K % 2 == 0)
-                {
-                    #pragma unroll
-                    for (int j = 0; j < K; j += 2)
-                    {
-                        uint2 v = *reinterpret_cast<const uint2*>(cp + j);
-                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y;
-                    }
-                }
-                else
-                {
-                    #pragma unroll
-                    for (int j = 0; j < K; ++j) w[tt][1 + j] = cp[j];
-                }
-            }
-            #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)          // last word of the preceding chunk (cyclic inside the tile)
-                w[tt][0] = __shfl_sync(0xffffffffu, w[tt][K], prev_lane);
-            mbar_wait(A_EMPTY(as), aph ^ 1);
-            tc_fence_after();
-            #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
-            {
-                const int t = 4 * tt + h;
-                uint32_t o[8];
-                if (p.knob & 1)
-                {
-                    #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = w[tt][j % (K + 1)];
-                }
-                else if (q & 1) decode16<K, cb, 1>(w[tt], o); else decode16<K, cb, 0>(w[tt], o);
-                if (!(p.knob & 2))
-                    tmem_st_32x32b_x8(tmem_base + lane_base + a_cols0 + as * TC_A_STAGE_COLS + 8 * t, o);
-                else if (o[0] == 0x12345678u && o[7] == 0x9abcdef0u) p.counters[0] = 1;     // keep the values alive
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
-            if (warp == TC_DEC_WARP0 && lane == 0) { if (u == 0) stamp(4); if (u == n_units - 1) stamp(10); }
-            if (++s == S) { s = 0; sph ^= 1; }
-            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            if (warp == TC_DEC_WARP0 && lane == 0 && u == 0) stamp(4);
+            if (q == 0 && lane == 0 && u == n_units - 1) stamp(10);
+            { const int t = s + s_step; const int c = t >= S; s = c ? t - S : t; sph ^= (s_wrap + c) & 1; }
+            { const int t = as + a_step; const int c = t >= p.a_stages; as = c ? t - p.a_stages : t; aph ^= (a_wrap + c) & 1; }
         }
     }
     else if (warp >= TC_EPI_WARP0)
@@ -382,7 +370,7 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const bool full = n_contrib == 1;
             float* my_part = p.ws + (size_t) (2 * blockIdx.x + (ubeg >= gs ? 0 : 1)) * part_stride;
 
-            mbar_wait<512>(D_FULL(dbuf), dphase);
+            mbar_wait<32>(D_FULL(dbuf), dphase);
             tc_fence_after();
             if (u == 0 && et == 0) stamp(7);
             const uint32_t d_addr = tmem_base + lane_base + d_cols0 + dbuf * p.NT;
@@ -469,6 +457,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out)
 {
+    const bool flat = (g_tc_knob & 16) != 0;     // experiment: contiguous 8-row boxes (wrong data, same bytes)
     static PFN_encodeTiled encode = nullptr;
     static std::mutex mu;
     struct Key { const void* p; int k, n, K; bool operator==(const Key& o) const { return p == o.p && k == o.k && n == o.n && K == o.K; } };
@@ -483,13 +472,15 @@ int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out)
         EXL3B_CHECK(fn && qres == cudaDriverEntryPointSuccess, EXL3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
         encode = (PFN_encodeTiled) fn;
     }
-    Key key{B, k, n, K};
+    Key key{B, flat ? -k : k, n, K};
     auto it = cache.find(key);
     if (it == cache.end())
     {
         CUtensorMap tm;
-        const cuuint64_t row_bytes = (cuuint64_t) (n / 16) * 32 * K;
-        cuuint64_t gdim[2] = { row_bytes / 8, (cuuint64_t) (k / 16) };
+        cuuint64_t row_bytes = (cuuint64_t) (n / 16) * 32 * K;
+        cuuint64_t rows = (cuuint64_t) (k / 16);
+        if (flat) { rows = rows * (n / 128); row_bytes = 256 * K; }
+        cuuint64_t gdim[2] = { row_bytes / 8, rows };
         cuuint64_t gstride[1] = { row_bytes };
         cuuint32_t box[2] = { (cuuint32_t) (32 * K), 8 };
         cuuint32_t estr[2] = { 1, 1 };
@@ -582,8 +573,10 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         p.m = m; p.k = a.k; p.n = a.n; p.NT = NT; p.c_fp32 = a.c_fp32; p.out_scale = a.out_scale;
         p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
         const bool small = NT <= 32;
-        p.tmem_cols = small ? 256 : 512;
-        p.a_stages = small ? 3 : 4;
+        // all of TMEM: the operand-stage loop (decode -> tcgen05.st -> MMA -> commit -> decode) has ~1.3 us of latency;
+        // the number of 64-column A stages in flight is what hides it (measured: 3 stages = 450 ns per unit floor)
+        p.tmem_cols = 512;
+        p.a_stages = NT <= 32 ? 7 : 4;
         p.d_bufs = NT <= 128 ? 2 : 1;
         p.b_load_bytes = m <= 8 ? 2048 : NT * 256;
         const int b_bytes = fused_x ? 2048 : NT * 256;       // m <= 8: only the first row group is ever written / needed
@@ -594,7 +587,7 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         if (stages < 2) stages = 2;
         p.stages = stages;
         p.dbg = g_tc_dbg;
-        p.knob = g_tc_knob;
+        p.knob_ = g_tc_knob;
         p.A_raw = fused_x ? a.A + (size_t) m0 * a.k : nullptr;
         p.suh = a.suh;
         p.b_bytes = b_bytes;
@@ -616,13 +609,6 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     }
     EXL3B_CUDA(cudaPeekAtLastError());
     return EXL3B_TAG_TC;
-}
-
-// dense hgemm on tcgen05: lands with the prefill work
-bool hgemm_tc_supported(int, int, int, int64_t) { return false; }
-int launch_hgemm_tc(cudaStream_t, const half*, const half*, void*, int, int, int, bool, int64_t)
-{
-    return fail(EXL3B_ERR_UNSUPPORTED, "tcgen05 hgemm not built");
 }
 
 }  // namespace exl3b

@@ -30,6 +30,7 @@ using namespace ptx;
 constexpr int I8_MAX_M = 4;
 constexpr int I8_A_STAGE_COLS = 128;
 constexpr int I8_A_STAGES = 3;
+constexpr int I8_DEC_GROUPS = 2;
 constexpr int I8_D_COL0 = I8_A_STAGES * I8_A_STAGE_COLS;      // 384
 constexpr int I8_NT = 16;                                      // N: rows 2r = hi digit, 2r+1 = lo digit of row r
 constexpr int I8_B_BYTES = 4096;                               // one row group: 32 K-chunks x (8 rows x 16 B)
@@ -37,9 +38,16 @@ constexpr int I8_B_STAGE = I8_B_BYTES + 64;                    // + per-row digi
 constexpr int I8_SUB_UNITS = 96;                               // int32 accumulator safety: <= 12288 k per accumulation
 constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 256 + 0  -> hi in [-127, 127]
 
-__host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int stages)
+// optional shared-memory cache of the whole transformed activation (m x k fp16) and of the per-block digit sums, filled by
+// the CTA prologue: the per-unit transform then is an 8-byte LDS + quantise instead of a global load + Hadamard
+// (measured: the two transform warps were the per-unit critical path, ~900 cycles of latency per unit each)
+constexpr int I8_CACHE_MAX_BYTES = 64 * 1024;
+
+__host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int stages, int cache_bytes)
 {
-    return tc_smem_layout(K, I8_B_STAGE, stages);
+    TcSmemLayout L = tc_smem_layout(K, I8_B_STAGE, stages);
+    L.total += cache_bytes;            // cache lives after the barrier block, at the old L.total
+    return L;
 }
 
 template <int K>
@@ -47,7 +55,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const TcSmemLayout L = i8_smem_layout(K, p.stages);
+    const TcSmemLayout L = i8_smem_layout(K, p.stages, 0);          // offsets only; the cache starts at L.total
+    const bool cached = p.b_load_bytes > 0;                            // host: cache_bytes (0 = recompute per unit)
+    half* xh_cache = reinterpret_cast<half*>(smem + L.total);
+    int* ts_cache = reinterpret_cast<int*>(smem + L.total + (size_t) p.m * p.k * 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
 
@@ -65,12 +76,26 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [I8_MAX_M] float bits, >= 0
     int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                            // [2][I8_MAX_M] digit sums per D buffer
 
+#ifdef EXL3B_TC_DEBUG
+    const int KNOB = p.knob_;
+#else
+    constexpr int KNOB = 0;
+#endif
+    auto stamp = [&](int slot)
+    {
+#ifdef EXL3B_TC_DEBUG
+        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[blockIdx.x * 64 + slot] = t; }
+#else
+        (void) slot;
+#endif
+    };
+    if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS + 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / I8_DEC_GROUPS + 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
         for (int r = 0; r < I8_MAX_M; ++r) s_absmax[r] = 0u;
         fence_barrier_init();
@@ -80,6 +105,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(1);
 
     const int KB = p.k / 128;
     const int strips = p.n / 128;
@@ -120,12 +146,37 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const int r = task / KB, kb = task % KB;
             float v[4];
             xh_block(r, kb, v);
+            if (cached)
+            {
+                const half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);     // exact: values are fp16
+                uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+                *reinterpret_cast<uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4) = o;
+            }
             float mx = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) atomicMax(&s_absmax[r], __float_as_uint(mx));
         }
         asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
+        if (cached)
+        {
+            // phase B: digit sums of every (row, k-block) with the now-known scale
+            for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
+            {
+                const int r = task / KB, kb = task % KB;
+                const float mxr = __uint_as_float(s_absmax[r]);
+                const float inv = mxr > 0.f ? (float) I8_QMAX / mxr : 0.f;
+                const uint2 raw = *reinterpret_cast<const uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4);
+                const half2 a = *reinterpret_cast<const half2*>(&raw.x), b = *reinterpret_cast<const half2*>(&raw.y);
+                int qs = __float2int_rn(__low2float(a) * inv) + __float2int_rn(__high2float(a) * inv) +
+                         __float2int_rn(__low2float(b) * inv) + __float2int_rn(__high2float(b) * inv);
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                if (lane == 0) ts_cache[r * KB + kb] = qs;
+            }
+            asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
+        }
+        if (warp == TC_DEC_WARP0 && lane == 0) stamp(2);
     }
 
     if (warp == 0)
@@ -138,7 +189,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         int s = 0, ph = 0;
         for (int u = 0; u < n_units; ++u)
         {
-            if (u >= S) mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+            if (u >= S) mbar_wait<64>(W_EMPTY(s), ph ^ 1);
             if (elect_one())
             {
                 mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
@@ -191,6 +242,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             }
             if (elect_one())
             {
+                if (!(KNOB & 4))
                 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                 {
@@ -226,15 +278,21 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         const int kstep = 2 % KB;
         for (int u = xw; u < n_units; u += 2)
         {
-            mbar_wait<256>(W_EMPTY(s), ph ^ 1);
+            mbar_wait<64>(W_EMPTY(s), ph ^ 1);
             uint8_t* dst = smem + L.off_b + s * L.b_bytes;
             #pragma unroll
             for (int r = 0; r < I8_MAX_M; ++r)
             {
-                if (r < p.m)
+                if (r < p.m && !(KNOB & 8))
                 {
                     float v[4];
-                    xh_block(r, kb, v);
+                    if (cached)
+                    {
+                        const uint2 raw = *reinterpret_cast<const uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4);
+                        const half2 a = *reinterpret_cast<const half2*>(&raw.x), b = *reinterpret_cast<const half2*>(&raw.y);
+                        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+                    }
+                    else xh_block(r, kb, v);
                     uint32_t hi_w[4], lo_w[4];
                     int qs = 0;
                     #pragma unroll
@@ -250,9 +308,16 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                     // chunk = lane (4 k-values x 4 bytes = 16 B), rows 2r (hi) and 2r+1 (lo) of row group 0
                     *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r) * 16) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
                     *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r + 1) * 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-                    #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
-                    if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
+                    if (cached)
+                    {
+                        if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = ts_cache[r * KB + kb];
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                        if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
+                    }
                 }
             }
             fence_proxy_async_smem();
@@ -265,64 +330,46 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     else if (warp < TC_EPI_WARP0)
     {
         // =========================== decode ===========================
-        const int q = warp & 3, h = (warp - TC_DEC_WARP0) >> 2;
+        // Two groups of eight warps (three 128-column TMEM operand stages only allow two units in decode at a time);
+        // group g owns the units u = g (mod 2); inside a group the two warps of a lane quarter take alternate k-tiles.
+        const int q = warp & 3, wi = (warp - TC_DEC_WARP0) >> 2;         // wi = 0..3
+        const int g = wi & 1, sub = wi >> 1;
         const int tl = strip_tile(q, lane), chunk = lane & 7;
         const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
-        int s = 0, sph = 0, as = 0, aph = 0;
-        for (int u = 0; u < n_units; ++u)
+        int s = g % S, sph = 0, as = g % I8_A_STAGES, aph = 0;
+        for (int u = g; u < n_units; u += I8_DEC_GROUPS)
         {
-            mbar_wait(W_FULL(s), sph);
+            mbar_wait<32>(W_FULL(s), sph);
+            if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
             const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
-            uint32_t w[TC_DEC_TILES][K + 1];
-            #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
-            {
-                const int t = 4 * tt + h;
-                const uint32_t* cp = wst + (t * 8 + tl) * (8 * K) + chunk * K;
-                if constexpr (K % 4 == 0)
-                {
-                    #pragma unroll
-                    for (int j = 0; j < K; j += 4)
-                    {
-                        uint4 v = *reinterpret_cast<const uint4*>(cp + j);
-                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y; w[tt][3 + j] = v.z; w[tt][4 + j] = v.w;
-                    }
-                }
-                else if constexpr (K % 2 == 0)
-                {
-                    #pragma unroll
-                    for (int j = 0; j < K; j += 2)
-                    {
-                        uint2 v = *reinterpret_cast<const uint2*>(cp + j);
-                        w[tt][1 + j] = v.x; w[tt][2 + j] = v.y;
-                    }
-                }
-                else
-                {
-                    #pragma unroll
-                    for (int j = 0; j < K; ++j) w[tt][1 + j] = cp[j];
-                }
-            }
-            #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
-                w[tt][0] = __shfl_sync(0xffffffffu, w[tt][K], prev_lane);
+            uint32_t w[4][K + 1];
+            tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub+2, sub+4, sub+6
             mbar_wait(A_EMPTY(as), aph ^ 1);
             tc_fence_after();
             #pragma unroll
-            for (int tt = 0; tt < TC_DEC_TILES; ++tt)
+            for (int j = 0; j < 4; ++j)
             {
-                const int t = 4 * tt + h;
+                const int t = sub + 2 * j;
                 uint32_t o[16];
-                if (q & 1) decode16_i8<K, 1>(w[tt], o); else decode16_i8<K, 0>(w[tt], o);
-                tmem_st_32x32b_x16(tmem_base + lane_base + as * I8_A_STAGE_COLS + 16 * t, o);
+                if (KNOB & 1)
+                {
+                    #pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = w[j][i % (K + 1)];
+                }
+                else if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
+                if (!(KNOB & 2))
+                    tmem_st_32x32b_x16(tmem_base + lane_base + as * I8_A_STAGE_COLS + 16 * t, o);
+                else if (o[0] == 0x12345678u && o[15] == 0x9abcdef0u) p.counters[0] = 1;
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
-            if (++s == S) { s = 0; sph ^= 1; }
-            if (++as == I8_A_STAGES) { as = 0; aph ^= 1; }
+            if (warp == TC_DEC_WARP0 && lane == 0 && u == 0) stamp(4);
+            if (q == 0 && sub == 0 && lane == 0 && u == n_units - 1) stamp(10);
+            s += I8_DEC_GROUPS; if (s >= S) { s -= S; sph ^= 1; }
+            as += I8_DEC_GROUPS; if (as >= I8_A_STAGES) { as -= I8_A_STAGES; aph ^= 1; }
         }
     }
     else
@@ -372,7 +419,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             for (int done = 0; done < seg; )
             {
                 const int sub = (seg - done) < I8_SUB_UNITS ? (seg - done) : I8_SUB_UNITS;
-                mbar_wait<512>(D_FULL(dbuf), dphase);
+                mbar_wait<32>(D_FULL(dbuf), dphase);
                 tc_fence_after();
                 uint32_t rr[16];
                 tmem_ld_32x32b_x16(tmem_base + lane_base + I8_D_COL0 + dbuf * I8_NT, rr);
@@ -440,6 +487,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             }
             u += seg;
         }
+        if (et == 0) stamp(8);
     }
 
     tc_fence_before();
@@ -486,13 +534,16 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     TcParams p{};
     p.B = a.B; p.C = a.C; p.svh = a.svh; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
-    p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob = g_tc_knob;
+    p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
     const int stage_bytes = 2048 * a.K + I8_B_STAGE;
-    int stages = (200 * 1024) / stage_bytes;
+    int cache_bytes = a.m * a.k * 2 + a.m * (a.k / 128) * 4;
+    cache_bytes = (cache_bytes + 127) / 128 * 128;
+    if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
+    int stages = (200 * 1024 - cache_bytes) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) stages = 2;
-    p.stages = stages; p.b_bytes = I8_B_STAGE;
-    const TcSmemLayout L = i8_smem_layout(a.K, stages);
+    p.stages = stages; p.b_bytes = I8_B_STAGE; p.b_load_bytes = cache_bytes;
+    const TcSmemLayout L = i8_smem_layout(a.K, stages, cache_bytes);
     EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): shared-memory budget exceeded");
     const long long U = (long long) (a.k / 128) * (a.n / 128);
     int grid = ctx->num_sms;

@@ -1,0 +1,271 @@
+// Dense fp16 GEMM on tcgen05 for the reconstruct -> hgemm prefill path:  C[m,n] = A[m,k] @ B[k,n], fp32 accumulate.
+// Replaces the reference's cuBLAS call (exllamav3_ext/hgemm.cu:19-102); no library GEMM is used.
+//
+//   * persistent CTAs, one 128(m) x 256(n) output tile at a time, K in steps of 64
+//   * warp 0: TMA producer (A box 128 x 64 K-major, B as four 64(k) x 64(n) boxes, both 128-byte swizzled) into a
+//     4-stage mbarrier ring;  warp 1: TMEM allocation + single-thread tcgen05.mma.kind::f16 issue (M=128, N=256, K=16,
+//     A K-major / B MN-major straight from the row-major operands, no transposes);  warps 4-7: epilogue
+//     (tcgen05.ld 32 columns at a time -> convert -> 16-byte row stores), overlapped with the next tile's MMAs through
+//     two TMEM accumulator buffers (2 x 256 columns = all of TMEM)
+//   * ragged m / n / k: TMA zero-fills out-of-bounds operand elements, stores are masked
+#include "tc_common.cuh"
+#include <unordered_map>
+#include <mutex>
+
+namespace exl3b {
+
+using namespace ptx;
+
+constexpr int HG_BM = 128, HG_BN = 256, HG_BK = 64, HG_STAGES = 4;
+constexpr int HG_A_BYTES = HG_BM * HG_BK * 2;          // 16 KB
+constexpr int HG_B_BYTES = HG_BK * HG_BN * 2;          // 32 KB
+constexpr int HG_THREADS = 256;
+
+struct HgParams
+{
+    void* C;
+    int m, k, n;
+    int c_fp32;
+    long long c_stride;
+    int tiles_m, tiles_n, k_iters;
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(HG_THREADS, 1)
+hgemm_tc_kernel(const HgParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sA = smem;                                   // HG_STAGES x 16 KB
+    uint8_t* sB = smem + HG_STAGES * HG_A_BYTES;          // HG_STAGES x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HG_STAGES * (HG_A_BYTES + HG_B_BYTES));
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (HG_STAGES + s); };
+    auto D_FULL = [&](int s) { return bar0 + 8u * (2 * HG_STAGES + s); };
+    auto D_EMPTY = [&](int s) { return bar0 + 8u * (2 * HG_STAGES + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HG_STAGES + 4);
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < HG_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0)
+    {
+        // =========================== TMA producer ===========================
+        if (elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+        const uint64_t pol = policy_evict_last();          // both operands are re-read by other CTAs: keep them in L2
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        int s = 0, ph = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        {
+            const int mb = t / p.tiles_n, nb = t % p.tiles_n;
+            for (int ki = 0; ki < p.k_iters; ++ki)
+            {
+                mbar_wait<32>(EMPTY(s), ph ^ 1);
+                if (elect_one())
+                {
+                    mbar_arrive_expect_tx(FULL(s), HG_A_BYTES + HG_B_BYTES);
+                    tma_load_2d(a0 + s * HG_A_BYTES, &tmA, ki * HG_BK, mb * HG_BM, FULL(s), pol);
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_2d(b0 + s * HG_B_BYTES + j * 8192, &tmB, nb * HG_BN + j * 64, ki * HG_BK, FULL(s), pol);
+                }
+                if (++s == HG_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp == 1)
+    {
+        // =========================== MMA issuer ===========================
+        const uint32_t idesc = idesc_f16_f32(HG_BM, HG_BN, /*b_mn_major=*/true);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        // A: K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO); LBO unused (1)
+        const uint64_t descA = smem_desc(0, 16, 1024, 2);
+        // B: MN-major, 128-byte swizzle: 64-column blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO)
+        const uint64_t descB = smem_desc(0, 8192, 1024, 2);
+        int s = 0, ph = 0, dbuf = 0, dph = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        {
+            mbar_wait(D_EMPTY(dbuf), dph ^ 1);
+            uint32_t acc = 0;
+            for (int ki = 0; ki < p.k_iters; ++ki)
+            {
+                mbar_wait(FULL(s), ph);
+                tc_fence_after();
+                if (elect_one())
+                {
+                    const uint32_t a_addr = a0 + s * HG_A_BYTES, b_addr = b0 + s * HG_B_BYTES;
+                    #pragma unroll
+                    for (int kk = 0; kk < HG_BK / 16; ++kk)
+                    {
+                        const uint64_t da = descA | (uint64_t) (((a_addr + kk * 32) >> 4) & 0x3fff);
+                        const uint64_t db = descB | (uint64_t) (((b_addr + kk * 2048) >> 4) & 0x3fff);
+                        mma_f16_ss(tb + dbuf * HG_BN, da, db, idesc, acc);
+                        acc = 1;
+                    }
+                    tc_commit(EMPTY(s));
+                    if (ki == p.k_iters - 1) tc_commit(D_FULL(dbuf));
+                }
+                acc = 1;
+                __syncwarp();
+                if (++s == HG_STAGES) { s = 0; ph ^= 1; }
+            }
+            dbuf ^= 1; if (dbuf == 0) dph ^= 1;
+        }
+        __syncwarp();
+    }
+    else if (warp >= 4)
+    {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        int dbuf = 0, dph = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        {
+            const int mb = t / p.tiles_n, nb = t % p.tiles_n;
+            const int row = mb * HG_BM + q * 32 + lane;
+            mbar_wait<32>(D_FULL(dbuf), dph);
+            tc_fence_after();
+            #pragma unroll 1
+            for (int c = 0; c < HG_BN / 32; ++c)
+            {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + dbuf * HG_BN + c * 32, r);
+                tc_wait_ld();
+                const int col0 = nb * HG_BN + c * 32;
+                if (row < p.m && col0 < p.n)
+                {
+                    if (p.c_fp32)
+                    {
+                        float* dst = (float*) p.C + (size_t) row * p.c_stride + col0;
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col0 + 4 * j < p.n)
+                                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    }
+                    else
+                    {
+                        half* dst = (half*) p.C + (size_t) row * p.c_stride + col0;
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            if (col0 + 8 * j < p.n)
+                            {
+                                uint4 o;
+                                half2 h;
+                                h = __floats2half2_rn(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])); o.x = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2half2_rn(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])); o.y = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2half2_rn(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])); o.z = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2half2_rn(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])); o.w = *reinterpret_cast<uint32_t*>(&h);
+                                *reinterpret_cast<uint4*>(dst + 8 * j) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(D_EMPTY(dbuf));
+            dbuf ^= 1; if (dbuf == 0) dph ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+    {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap_fp16_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
+                             uint32_t box_outer, CUtensorMap* out)
+{
+    static PFN_encodeTiled2 encode = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode)
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        EXL3B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        EXL3B_CHECK(fn && qres == cudaDriverEntryPointSuccess, EXL3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        encode = (PFN_encodeTiled2) fn;
+    }
+    cuuint64_t gdim[2] = { inner, outer };
+    cuuint64_t gstride[1] = { row_stride_bytes };
+    cuuint32_t box[2] = { box_inner, box_outer };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EXL3B_CHECK(r == CUDA_SUCCESS, EXL3B_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for hgemm operand", (int) r);
+    return 0;
+}
+
+bool hgemm_tc_supported(int m, int k, int n, int64_t c_stride)
+{
+    // TMA needs 16-byte aligned row pitches; the epilogue stores 16-byte vectors
+    return m >= 1 && k >= 8 && n >= 8 && k % 8 == 0 && n % 8 == 0 && c_stride % 8 == 0;
+}
+
+int launch_hgemm_tc(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,
+                    int64_t c_stride)
+{
+    EXL3B_CHECK(((uintptr_t) a & 15) == 0 && ((uintptr_t) b & 15) == 0 && ((uintptr_t) c & 15) == 0, EXL3B_ERR_ARG,
+                "hgemm: operands must be 16-byte aligned");
+    CUtensorMap tmA, tmB;
+    int r = make_tmap_fp16_2d(a, (uint64_t) k, (uint64_t) m, (uint64_t) k * 2, HG_BK, HG_BM, &tmA); if (r) return r;
+    r = make_tmap_fp16_2d(b, (uint64_t) n, (uint64_t) k, (uint64_t) n * 2, 64, HG_BK, &tmB); if (r) return r;
+    HgParams p{};
+    p.C = c; p.m = m; p.k = k; p.n = n; p.c_fp32 = c_fp32; p.c_stride = c_stride;
+    p.tiles_m = (m + HG_BM - 1) / HG_BM; p.tiles_n = (n + HG_BN - 1) / HG_BN; p.k_iters = (k + HG_BK - 1) / HG_BK;
+    static bool attr_set[32] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    const int smem_bytes = HG_STAGES * (HG_A_BYTES + HG_B_BYTES) + 256;
+    if (!attr_set[dev & 31])
+    {
+        EXL3B_CUDA(cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set[dev & 31] = true;
+    }
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = p.tiles_m * p.tiles_n; if (grid > sms) grid = sms;
+    hgemm_tc_kernel<<<grid, HG_THREADS, smem_bytes, stream>>>(p, tmA, tmB);
+    count_launch();
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return 0;
+}
+
+}  // namespace exl3b

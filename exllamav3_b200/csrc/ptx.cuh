@@ -54,18 +54,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall-clock
 // (%globaltimer, checked every 1024 polls), not an iteration count: try_wait returns early whenever ANY barrier
 // activity wakes the warp, so iteration counts say nothing about elapsed time.
-// SLEEP_NS > 0 adds an explicit back-off for roles whose waits are long and not latency critical (epilogue waiting
-// for a whole segment, producer waiting for a free ring slot): polling warps otherwise burn issue slots the decode
-// warps need (measured: ~12 % of all issued instructions came from four epilogue warps polling every ~30 ns).
-template <int SLEEP_NS = 0>
+// BACKOFF_NS > 0: exponential back-off (BACKOFF_NS, 2x, ... capped at 16x) between polls for roles whose waits can be
+// long: polling warps otherwise burn issue slots the decode warps need (measured: ~40 % of all issued instructions of
+// the first version of the kernel were polls; profiles/r01_ncu_notes.md).
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     unsigned long long t0 = 0;
+    [[maybe_unused]] uint32_t ns = BACKOFF_NS;
     while (!mbar_try_wait(bar, parity))
     {
-        if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if constexpr (BACKOFF_NS > 0) { __nanosleep(ns); if (ns < 16u * BACKOFF_NS) ns <<= 1; }
         if ((++polls & 1023u) == 0)
         {
             unsigned long long t;

@@ -12,7 +12,7 @@ constexpr int TC_THREADS = 768;
 constexpr int TC_XF_WARP0 = 2;               // warps 2,3: in-kernel input transform (small m)
 constexpr int TC_DEC_WARP0 = 4;
 constexpr int TC_DEC_WARPS = 16;             // 4 per lane quarter: tiles {h, h+4} of every unit
-constexpr int TC_DEC_TILES = 8 * 4 / TC_DEC_WARPS;
+constexpr int TC_DEC_GROUPS = 4;             // exact path: groups of 4 warps, each owning every 4th unit
 constexpr int TC_EPI_WARP0 = TC_DEC_WARP0 + TC_DEC_WARPS;
 constexpr int TC_MAX_STAGES = 16;
 constexpr int TC_A_STAGE_COLS = 64;          // 128 k-values x fp16, 2 per 32-bit TMEM column
@@ -36,7 +36,7 @@ struct TcParams
     int tmem_cols;               // 256 or 512
     const half* A_raw;           // fused input transform (m <= 8): raw activations (m, k) and suh; null -> xh_tiled is used
     const half* suh;
-    int knob;                    // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA
+    int knob_;                   // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA
     unsigned long long* dbg;     // optional per-CTA timeline (16 x u64 per CTA), bring-up only
 };
 
@@ -61,6 +61,45 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int K, int b_bytes, int s
 __device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
 __device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
 
+
+// Load the K+1 words (chunk + preceding word, the latter by shuffle from the neighbouring lane) of four tiles
+// t0, t0 + tstride, ... of this lane's (tile-in-strip, chunk) from a weight stage in shared memory.
+template <int K>
+__device__ __forceinline__ void tc_load_tiles4(const uint32_t* wst, int tl, int chunk, int prev_lane, int t0, int tstride,
+                                               uint32_t (&w)[4][K + 1])
+{
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const uint32_t* cp = wst + ((t0 + tstride * j) * 8 + tl) * (8 * K) + chunk * K;
+        if constexpr (K % 4 == 0)
+        {
+            #pragma unroll
+            for (int i = 0; i < K; i += 4)
+            {
+                uint4 v = *reinterpret_cast<const uint4*>(cp + i);
+                w[j][1 + i] = v.x; w[j][2 + i] = v.y; w[j][3 + i] = v.z; w[j][4 + i] = v.w;
+            }
+        }
+        else if constexpr (K % 2 == 0)
+        {
+            #pragma unroll
+            for (int i = 0; i < K; i += 2)
+            {
+                uint2 v = *reinterpret_cast<const uint2*>(cp + i);
+                w[j][1 + i] = v.x; w[j][2 + i] = v.y;
+            }
+        }
+        else
+        {
+            #pragma unroll
+            for (int i = 0; i < K; ++i) w[j][1 + i] = cp[i];
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+        w[j][0] = __shfl_sync(0xffffffffu, w[j][K], prev_lane);      // last word of the preceding chunk (cyclic in the tile)
+}
 
 int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out);
 extern unsigned long long* g_tc_dbg;

@@ -14,23 +14,49 @@ A = torch.randn((m, k), generator=g, device=dev).half(); Ah = torch.empty_like(A
 C = torch.empty((m, n), dtype=torch.half, device=dev)
 ext.set_gemm_path(ext.EXL3B_TAG_TC)
 ext.lib.exl3b_debug_tc_knob(knob)
-dbg = torch.zeros((148, 16), dtype=torch.int64, device=dev)
+dbgs = [torch.zeros((148, 64), dtype=torch.int64, device=dev) for _ in range(iters)]
 ext.lib.exl3b_debug_tc_timeline.argtypes = [ctypes.c_void_p]
-for i in range(iters):
-    if i == iters - 1:
-        ext.lib.exl3b_debug_tc_timeline(dbg.data_ptr())
+path = int(os.environ.get("EXL3B_PATH", "0"))
+ext.set_gemm_path(path)
+# a CUDA graph of the back-to-back launches, like the benchmark
+for i in range(2):
     ext.exl3_gemm(A, Bs[i], C, su, Ah, sv, -1, False, True, 0)
 torch.cuda.synchronize()
-ext.lib.exl3b_debug_tc_timeline(None)
-d = dbg.cpu().numpy().astype(np.int64)
-d = d[d[:, 0] > 0]
-t0 = d[:, 0].min()
-names = {0: "entry", 1: "setup done", 2: "producer first batch issued", 3: "decode: first W_FULL", 4: "decode: first unit done",
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=st):
+        for i in range(iters):
+            ext.lib.exl3b_debug_tc_timeline(dbgs[i].data_ptr())
+            ext.exl3_gemm(A, Bs[i], C, su, Ah, sv, -1, False, True, 0)
+    ext.lib.exl3b_debug_tc_timeline(None)
+    gr.replay(); torch.cuda.synchronize()
+    gr.replay()
+torch.cuda.synchronize()
+names = {0: "entry", 1: "setup done", 2: "prologue done", 3: "decode: first W_FULL", 4: "decode: first unit done",
          5: "mma: first operands ready", 6: "mma: last commit", 10: "decode: last unit done", 7: "epi: first D_FULL",
-         8: "epi: done", 9: "teardown"}
-print(f"knob={knob} shape k={k} n={n} K={K} m={m}: {len(d)} CTAs; ns relative to the earliest CTA entry (min / median / max)")
-for s in (0, 1, 2, 3, 4, 5, 10, 6, 7, 8, 9):
-    v = d[:, s] - t0
-    v = v[d[:, s] > 0]
-    if len(v):
-        print(f"  {names[s]:32s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
+         8: "epi: done"}
+D = [d.cpu().numpy().astype(np.int64) for d in dbgs]
+t0 = min(d[d[:, 0] > 0][:, 0].min() for d in D)
+print(f"knob={knob} path={path} shape k={k} n={n} K={K} m={m}: {iters} graph-replayed launches; ns since the first entry of launch 0 (min / median / max over CTAs)")
+for i, d in enumerate(D):
+    d = d[d[:, 0] > 0]
+    print(f" launch {i}")
+    for s in (0, 1, 2, 3, 4, 5, 10, 6, 7, 8):
+        v = d[:, s]; v = v[v > 0] - t0
+        if len(v):
+            print(f"  {names[s]:28s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
+
+# fine-grained decode-warp stamps (exact kernel only): units 8..11 of each CTA, warp 4 lane 0
+d = D[3]
+if (d[:, 16] > 0).any():
+    lab = ["loop top", "after W_FULL wait", "after LDS+SHFL", "after A_EMPTY wait", "after decode+STTM issue", "after wait::st", "after arrive"]
+    print(" decode warp 4, launch 3: median ns since loop top of unit 8")
+    base = d[:, 16]
+    for uu in range(4):
+        row = []
+        for i in range(7):
+            v = d[:, 16 + uu * 8 + i] - base
+            v = v[d[:, 16 + uu * 8 + i] > 0]
+            row.append(int(np.median(v)) if len(v) else -1)
+        print("  unit", 8 + uu, dict(zip(lab, row)))
