@@ -338,8 +338,13 @@ def run_gpu_arm(args, cfg):
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # Tear-down order matters: a CUDA graph holding captured NCCL kernels must die before the communicator, and
+        # destroy_process_group() has been seen to hang after graph-captured collectives -- leave without it.
+        del graph
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
