@@ -400,19 +400,19 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 
             if (!full)
             {
-                __threadfence();
-                epi_bar();
+                epi_bar();                                    // all partial stores of this CTA are ordered before ...
                 if (et == 0)
                 {
+                    __threadfence();                          // ... this single gpu-scope fence + the arrival count (cumulativity)
                     const int old = atomicAdd(&p.counters[strip], 1);
                     const int last = old == n_contrib - 1;
-                    if (last) p.counters[strip] = 0;          // self-reset for the next launch using this slot
+                    if (last) { p.counters[strip] = 0; __threadfence(); }          // self-reset for the next launch using this slot
                     *s_flag = last;
                 }
                 epi_bar();
                 if (*s_flag)
                 {
-                    __threadfence();
+                    const int which_a = unit_begin(U, G, c_a) >= gs ? 0 : 1;       // only c_a can have started in an earlier strip
                     for (int c0 = 0; c0 < p.m; c0 += 16)
                     {
                         float acc[16];
@@ -420,10 +420,12 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
                         for (int c = c_a; c <= c_b; ++c)                 // fixed order: deterministic
                         {
-                            const float* part = p.ws + (size_t) (2 * c + (unit_begin(U, G, c) >= gs ? 0 : 1)) * part_stride;
+                            const float* part = p.ws + (size_t) (2 * c + (c == c_a ? which_a : 0)) * part_stride;
+                            float v[16];
                             #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < p.m) acc[j] += __ldcg(part + (c0 + j) * 128 + col);
+                            for (int j = 0; j < 16; ++j) v[j] = (c0 + j < p.m) ? __ldcg(part + (c0 + j) * 128 + col) : 0.f;
+                            #pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] += v[j];
                         }
                         #pragma unroll
                         for (int j = 0; j < 16; ++j) tile[j * 128 + col] = acc[j];

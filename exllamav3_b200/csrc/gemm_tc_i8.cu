@@ -58,7 +58,6 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const TcSmemLayout L = i8_smem_layout(K, p.stages, 0);          // offsets only; the cache starts at L.total
     const bool cached = p.b_load_bytes > 0;                            // host: cache_bytes (0 = recompute per unit)
     half* xh_cache = reinterpret_cast<half*>(smem + L.total);
-    int* ts_cache = reinterpret_cast<int*>(smem + L.total + (size_t) p.m * p.k * 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
 
@@ -158,24 +157,6 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (lane == 0) atomicMax(&s_absmax[r], __float_as_uint(mx));
         }
         asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
-        if (cached)
-        {
-            // phase B: digit sums of every (row, k-block) with the now-known scale
-            for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
-            {
-                const int r = task / KB, kb = task % KB;
-                const float mxr = __uint_as_float(s_absmax[r]);
-                const float inv = mxr > 0.f ? (float) I8_QMAX / mxr : 0.f;
-                const uint2 raw = *reinterpret_cast<const uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4);
-                const half2 a = *reinterpret_cast<const half2*>(&raw.x), b = *reinterpret_cast<const half2*>(&raw.y);
-                int qs = __float2int_rn(__low2float(a) * inv) + __float2int_rn(__high2float(a) * inv) +
-                         __float2int_rn(__low2float(b) * inv) + __float2int_rn(__high2float(b) * inv);
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
-                if (lane == 0) ts_cache[r * KB + kb] = qs;
-            }
-            asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
-        }
         if (warp == TC_DEC_WARP0 && lane == 0) stamp(2);
     }
 
@@ -308,16 +289,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                     // chunk = lane (4 k-values x 4 bytes = 16 B), rows 2r (hi) and 2r+1 (lo) of row group 0
                     *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r) * 16) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
                     *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r + 1) * 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-                    if (cached)
-                    {
-                        if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = ts_cache[r * KB + kb];
-                    }
-                    else
-                    {
-                        #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
-                        if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
-                    }
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                    if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
                 }
             }
             fence_proxy_async_smem();
@@ -421,6 +395,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 const int sub = (seg - done) < I8_SUB_UNITS ? (seg - done) : I8_SUB_UNITS;
                 mbar_wait<32>(D_FULL(dbuf), dphase);
                 tc_fence_after();
+                if (et == 0 && u + seg >= n_units) stamp(7);
                 uint32_t rr[16];
                 tmem_ld_32x32b_x16(tmem_base + lane_base + I8_D_COL0 + dbuf * I8_NT, rr);
                 tc_wait_ld();
@@ -454,33 +429,48 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             {
                 #pragma unroll
                 for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) my_part[r * 128 + col] = facc[r];
-                __threadfence();
-                epi_bar();
+                epi_bar();                                    // all partial stores of this CTA are ordered before ...
+                if (et == 0 && u + seg >= n_units) stamp(11);
                 if (et == 0)
                 {
+                    __threadfence();                          // ... this single gpu-scope fence + the arrival count (cumulativity)
                     const int old = atomicAdd(&p.counters[strip], 1);
                     const int last = old == n_contrib - 1;
-                    if (last) p.counters[strip] = 0;
+                    if (last) { p.counters[strip] = 0; __threadfence(); }
                     *s_flag = last;
                 }
                 epi_bar();
+                if (et == 0 && u + seg >= n_units) stamp(12);
                 if (*s_flag)
                 {
-                    __threadfence();
+                    // contributors c_a..c_b in fixed order (deterministic); slot = 2c + (first segment of c ? 0 : 1).
+                    // Only c_a can have started in an earlier strip.  All loads are issued before the first add.
                     #pragma unroll
                     for (int r = 0; r < I8_MAX_M; ++r)
                     {
                         if (r < p.m)
                         {
                             float a = 0.f;
-                            for (int c = c_a; c <= c_b; ++c)                 // fixed order: deterministic
+                            const int which_a = unit_begin(U, G, c_a) >= gs ? 0 : 1;
+                            int c = c_a;
+                            while (c <= c_b)
                             {
-                                const float* part = p.ws + (size_t) (2 * c + (unit_begin(U, G, c) >= gs ? 0 : 1)) * part_stride;
-                                a += __ldcg(part + r * 128 + col);
+                                float v[8];
+                                #pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                {
+                                    const int cc = c + j;
+                                    const int which = cc == c_a ? which_a : 0;
+                                    v[j] = cc <= c_b ? __ldcg(p.ws + (size_t) (2 * cc + which) * part_stride + r * 128 + col) : 0.f;
+                                }
+                                #pragma unroll
+                                for (int j = 0; j < 8; ++j) a += v[j];
+                                c += 8;
                             }
                             tile[r * 128 + col] = a;
                         }
                     }
+                    if (et == 0 && u + seg >= n_units) stamp(13);
                     emit_rows(strip);
                 }
                 epi_bar();
@@ -536,7 +526,7 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
     p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
     const int stage_bytes = 2048 * a.K + I8_B_STAGE;
-    int cache_bytes = a.m * a.k * 2 + a.m * (a.k / 128) * 4;
+    int cache_bytes = a.m * a.k * 2;
     cache_bytes = (cache_bytes + 127) / 128 * 128;
     if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
     int stages = (200 * 1024 - cache_bytes) / stage_bytes;

@@ -35,14 +35,14 @@ with torch.cuda.stream(st):
 torch.cuda.synchronize()
 names = {0: "entry", 1: "setup done", 2: "prologue done", 3: "decode: first W_FULL", 4: "decode: first unit done",
          5: "mma: first operands ready", 6: "mma: last commit", 10: "decode: last unit done", 7: "epi: first D_FULL",
-         8: "epi: done"}
+         8: "epi: done", 11: "epi: partial written+fence", 12: "epi: counter known", 13: "epi(last): partials summed"}
 D = [d.cpu().numpy().astype(np.int64) for d in dbgs]
 t0 = min(d[d[:, 0] > 0][:, 0].min() for d in D)
 print(f"knob={knob} path={path} shape k={k} n={n} K={K} m={m}: {iters} graph-replayed launches; ns since the first entry of launch 0 (min / median / max over CTAs)")
 for i, d in enumerate(D):
     d = d[d[:, 0] > 0]
     print(f" launch {i}")
-    for s in (0, 1, 2, 3, 4, 5, 10, 6, 7, 8):
+    for s in (0, 1, 2, 3, 4, 5, 10, 6, 7, 11, 12, 13, 8):
         v = d[:, s]; v = v[v > 0] - t0
         if len(v):
             print(f"  {names[s]:28s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
