@@ -298,6 +298,16 @@ def run_gpu_arm(args, cfg):
 
     peak, peak_src = read_peaks()
     achieved = tok.alg_bytes / (ms_per_step * 1e-3) / 1e9          # per rank (each rank streams its own shard)
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/): measured bytes / algorithmic bytes
+    # of the captured launch, applied to the average launch of this step
+    traffic = None
+    try:
+        import csv
+        cap = {r[0]: r[2] for r in csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_i8_gate_4096x14336_K4_m1.csv"))) if len(r) == 3}
+        rd = float(cap["dram__bytes_read.sum"]) * 1e6 + float(cap["dram__bytes_write.sum"])
+        traffic = rd / alg_bytes(1, 4096, 14336, 4, True) * tok.alg_bytes / len(tok.mats)
+    except Exception:
+        pass
     cpu_baseline = None
     check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,8 +337,10 @@ def run_gpu_arm(args, cfg):
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
                        "cuda_graph": graph is not None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "algorithmic bytes of the whole step / step time (all launches incl. input transforms)"},
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "gemm_tc_i8_kernel (tcgen05 kind::i8 decode-GEMM)",
+                         "note": "achieved = algorithmic bytes of the step / step time = average over the step's launches of the "
+                                 "dominant kernel (it is 100 % of the launches, profiles/r01_launches.md); traffic = bytes per average "
+                                 "launch scaled from the ncu --set full capture in profiles/ (measured/algorithmic = 1.0006)"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "tok/s", "h2d_bytes_per_step": hx.numel() * 2,
                     "d2h_bytes_per_step": hlogits.numel() * hlogits.element_size()},
