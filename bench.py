@@ -174,7 +174,7 @@ def run_reference_arm(args, cfg):
 class Token:
     """All quantized linears of one token for one TP rank, with their input/output/scratch buffers."""
 
-    def __init__(self, cfg, tp, rank, dev, seed=1234):
+    def __init__(self, cfg, tp, rank, dev, seed=1234, fuse=True):
         import torch
         from exllamav3_b200 import ext
         self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
@@ -196,14 +196,37 @@ class Token:
             self.alg_bytes += alg_bytes(1, k, n, K, c_fp32)
         self.first_x = self.mats[0]["x"]
         self.logits = self.mats[-1]["y"]
+        # launch list.  k+v and gate+up share their input and shape: the reference's model code issues them as ONE
+        # exl3_mgemm each at bsz*q_len <= 32 (modules/attn.py:603-631 multi_kv, modules/mlp.py:726-760 multi_gu)
+        self.launches = []
+        i = 0
+        while i < len(self.mats):
+            a = self.mats[i]
+            b = self.mats[i + 1] if i + 1 < len(self.mats) else None
+            if fuse and b is not None and (a["name"], b["name"]) in (("k", "v"), ("gate", "up")) and a["layer"] == b["layer"]:
+                ptr = lambda key: torch.tensor([a[key].data_ptr(), b[key].data_ptr()], dtype=torch.long, device=dev)
+                y2 = torch.empty((2, 1, a["n"]), dtype=a["y"].dtype, device=dev)
+                xh2 = torch.empty((2, 1, a["k"]), dtype=torch.half, device=dev)
+                self.launches.append(dict(kind="mgemm", x=a["x"].view(1, 1, -1), y=y2, xh=xh2, K=a["K"], reduce=False,
+                                          B=ptr("tr"), suh=ptr("suh"), svh=ptr("svh")))
+                self.alg_bytes -= 2 * a["k"]            # the shared input is read once
+                i += 2
+            else:
+                self.launches.append(dict(kind="gemm", mt=a, reduce=a["reduce"]))
+                i += 1
 
     def run(self):
         ext, dist = self.ext, None
-        for mt in self.mats:
-            ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
-            if mt["reduce"]:
-                import torch.distributed as dist
-                dist.all_reduce(mt["y"])
+        for ln in self.launches:
+            if ln["kind"] == "gemm":
+                mt = ln["mt"]
+                ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
+                if mt["reduce"]:
+                    import torch.distributed as dist
+                    dist.all_reduce(mt["y"])
+            else:
+                ext.exl3_mgemm(ln["x"], ln["B"], ln["y"], ln["suh"], ln["xh"], ln["svh"], None, None, ln["K"], -1,
+                               False, True, -1, -1, 0)
 
 
 def run_gpu_arm(args, cfg):
@@ -221,7 +244,7 @@ def run_gpu_arm(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     from exllamav3_b200 import ext
 
-    tok = Token(cfg, world, rank, dev)
+    tok = Token(cfg, world, rank, dev, fuse=not args.no_fuse)
     stream = torch.cuda.Stream(device=dev)
     launches0 = ext.launch_count()
     with torch.cuda.stream(stream):
@@ -305,7 +328,7 @@ def run_gpu_arm(args, cfg):
         import csv
         cap = {r[0]: r[2] for r in csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_i8_gate_4096x14336_K4_m1.csv"))) if len(r) == 3}
         rd = float(cap["dram__bytes_read.sum"]) * 1e6 + float(cap["dram__bytes_write.sum"])
-        traffic = rd / alg_bytes(1, 4096, 14336, 4, True) * tok.alg_bytes / len(tok.mats)
+        traffic = rd / alg_bytes(1, 4096, 14336, 4, True) * tok.alg_bytes / len(tok.launches)
     except Exception:
         pass
     cpu_baseline = None
@@ -332,7 +355,9 @@ def run_gpu_arm(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.model} EXL3 4.0bpw (lm_head 6bpw) b=1 decode: "
-                                   f"{len(tok.mats)} qgemms/token, m=1, mul1 codebook, random-init trellis",
+                                   f"{len(tok.mats)} quantized matrices/token in {len(tok.launches)} launches "
+                                   f"(k+v and gate+up as exl3_mgemm like the reference's decode path), m=1, mul1 codebook, "
+                                   f"random-init trellis",
                        "parallelism": f"tp{world}" if world > 1 else "single",
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
                        "cuda_graph": graph is not None},
@@ -367,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3.1-8b", choices=list(MODELS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

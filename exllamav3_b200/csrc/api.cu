@@ -54,6 +54,7 @@ int get_ctx(DevCtx** out)
         EXL3B_CUDA(cudaMalloc(&c.counters, sizeof(int) * DevCtx::NUM_SLOTS * DevCtx::COUNTERS_PER_SLOT));
         EXL3B_CUDA(cudaMemset(c.counters, 0, sizeof(int) * DevCtx::NUM_SLOTS * DevCtx::COUNTERS_PER_SLOT));
         EXL3B_CUDA(cudaMalloc(&c.tabs, sizeof(MSlotTable) * DevCtx::NUM_SLOTS));
+        EXL3B_CUDA(cudaMalloc(&c.tmap_slots, (size_t) DevCtx::NUM_SLOTS * DevCtx::TMAP_SLOTS * 128));
         EXL3B_CUDA(cudaDeviceSynchronize());
         c.device = dev;
     }
@@ -238,6 +239,9 @@ int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, co
     a.bszm_in = bszm_in; a.bszm_out = bszm_out; a.m = m; a.k = k; a.n = n; a.K = K; a.cb = cb;
     a.c_fp32 = c_fp32 != 0; a.min_index = min_index; a.max_index = max_index; a.num_tokens = num_tokens;
     a.size_n_list = size_n_list; a.c_ptrs = c_ptrs; a.num_c_ptrs = num_c_ptrs;
+    const int path = g_force_path.load();
+    if ((path == 0 || path == EXL3B_TAG_TC_I8) && mgemm_tc_i8_supported(ctx, a))
+        return launch_mgemm_tc_i8((cudaStream_t) stream, ctx, a);
     return launch_mgemm((cudaStream_t) stream, ctx, a);
 }
 

@@ -48,6 +48,9 @@ struct DevCtx
     size_t xh_tiled_slot_bytes = 0;
     half* xh_scratch = nullptr;   // input-transform scratch when the caller passes A_had = NULL
     size_t xh_scratch_elems = 0;
+    uint8_t* tmap_slots = nullptr;   // NUM_SLOTS x TMAP_SLOTS x 128 B: per-CTA patched tensor maps of multi-matrix launches
+    static constexpr int TMAP_SLOTS = 256;
+    uint8_t* tmap_slot(int s) { return tmap_slots + (size_t) s * TMAP_SLOTS * 128; }
     uint64_t launch_seq = 0;
     int next_slot() { return (int) (launch_seq++ % NUM_SLOTS); }
     float* ws_slot(int s) { return (float*) ((char*) ws + (size_t) s * WS_BYTES_PER_SLOT); }
@@ -83,6 +86,9 @@ int launch_gemm_simt(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 bool gemm_tc_supported(const GemmArgs& a);
 int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+struct MGemmArgs;
+bool mgemm_tc_i8_supported(const DevCtx* ctx, const MGemmArgs& a);
+int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
 bool gemm_tc_i8_supported(const GemmArgs& a);
 
 struct MGemmArgs

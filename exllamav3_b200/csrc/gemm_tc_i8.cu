@@ -61,6 +61,20 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
 
+    // multi-matrix launch (exl3_mgemm): group `mat` of g_per_mat CTAs works on matrix `mat` exactly like a single-matrix
+    // launch of g_per_mat CTAs; `cta` is the index inside the group
+    int cta = blockIdx.x, G = gridDim.x, mat = 0;
+    const half* suh = p.suh; const half* svh = p.svh; const half* A_raw = p.A_raw;
+    char* Cout = (char*) p.C; float* ws = p.ws; int* counters = p.counters;
+    const bool multi = p.num_mats > 0;
+    if (multi)
+    {
+        G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G;
+        suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
+        A_raw += (size_t) mat * p.a_mat_stride; Cout += (size_t) mat * p.c_mat_stride;
+        ws += (size_t) mat * 2 * G * (I8_MAX_M * 128); counters += mat * (p.n / 128);
+    }
+
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     const uint32_t bar0 = smem_u32(bars);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -109,18 +123,17 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const int KB = p.k / 128;
     const int strips = p.n / 128;
     const long long U = (long long) KB * strips;
-    const int G = gridDim.x;
-    const long long ubeg = unit_begin(U, G, blockIdx.x), uend = unit_begin(U, G, blockIdx.x + 1);
+    const long long ubeg = unit_begin(U, G, cta), uend = unit_begin(U, G, cta + 1);
     const int n_units = (int) (uend - ubeg);
 
     // fp16 transformed activation of (row r, k-block kb), 4 values per lane, exactly as the reference's A_had
     auto xh_block = [&](int r, int kb, float (&v)[4])
     {
-        uint2 raw = *reinterpret_cast<const uint2*>(p.A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
+        uint2 raw = *reinterpret_cast<const uint2*>(A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
         half2 a = *reinterpret_cast<half2*>(&raw.x), b = *reinterpret_cast<half2*>(&raw.y);
-        if (p.suh)
+        if (suh)
         {
-            const uint2 scb = *reinterpret_cast<const uint2*>(p.suh + kb * 128 + lane * 4);
+            const uint2 scb = *reinterpret_cast<const uint2*>(suh + kb * 128 + lane * 4);
             a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
             b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
             float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
@@ -163,7 +176,18 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     if (warp == 0)
     {
         // =========================== producer ===========================
-        if (elect_one()) prefetch_tmap(&tmap_w);
+        const void* tm = &tmap_w;
+        if (multi)
+        {
+            // per-CTA tensor map: the template (dims / strides / box of this shape) with matrix `mat`'s address
+            uint8_t* stm = smem + ((L.off_bars + 640 + 127) & ~127);
+            reinterpret_cast<uint32_t*>(stm)[lane] = reinterpret_cast<const uint32_t*>(&tmap_w)[lane];
+            __syncwarp();
+            void* gtm = p.tmap_slots + (size_t) blockIdx.x * 128;
+            tmap_patch_address(smem_u32(stm), gtm, p.B_ptrs[mat], lane);
+            tm = gtm;
+        }
+        else if (elect_one()) prefetch_tmap(&tmap_w);
         const uint64_t pol_w = policy_evict_first();
         const uint32_t w_smem0 = smem_u32(smem);
         int strip = (int) (ubeg / KB), kb = (int) (ubeg % KB);
@@ -174,7 +198,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (elect_one())
             {
                 mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
-                tma_load_2d(w_smem0 + s * L.w_bytes, &tmap_w, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
+                tma_load_2d(w_smem0 + s * L.w_bytes, tm, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
             }
             if (++kb == KB) { kb = 0; ++strip; }
             if (++s == S) { s = 0; ph ^= 1; }
@@ -368,8 +392,8 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         {
             epi_bar();
             if (q < p.m)
-                output_row_128(tile + q * 128, (char*) p.C, (size_t) q * p.n + strip * 128,
-                               p.svh ? p.svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
+                output_row_128(tile + q * 128, Cout, (size_t) q * p.n + strip * 128,
+                               svh ? svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
             epi_bar();
         };
 
@@ -385,7 +409,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + KB - 1);
             const int n_contrib = c_b - c_a + 1;
             const bool full = n_contrib == 1;
-            float* my_part = p.ws + (size_t) (2 * blockIdx.x + (ubeg >= gs ? 0 : 1)) * part_stride;
+            float* my_part = ws + (size_t) (2 * cta + (ubeg >= gs ? 0 : 1)) * part_stride;
 
             float facc[I8_MAX_M];
             #pragma unroll
@@ -434,9 +458,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 if (et == 0)
                 {
                     __threadfence();                          // ... this single gpu-scope fence + the arrival count (cumulativity)
-                    const int old = atomicAdd(&p.counters[strip], 1);
+                    const int old = atomicAdd(&counters[strip], 1);
                     const int last = old == n_contrib - 1;
-                    if (last) { p.counters[strip] = 0; __threadfence(); }
+                    if (last) { counters[strip] = 0; __threadfence(); }
                     *s_flag = last;
                 }
                 epi_bar();
@@ -461,7 +485,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                                 {
                                     const int cc = c + j;
                                     const int which = cc == c_a ? which_a : 0;
-                                    v[j] = cc <= c_b ? __ldcg(p.ws + (size_t) (2 * cc + which) * part_stride + r * 128 + col) : 0.f;
+                                    v[j] = cc <= c_b ? __ldcg(ws + (size_t) (2 * cc + which) * part_stride + r * 128 + col) : 0.f;
                                 }
                                 #pragma unroll
                                 for (int j = 0; j < 8; ++j) a += v[j];
@@ -540,6 +564,69 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
     if (grid > U) grid = (int) U;
     EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+    cudaError_t err = cudaSuccess;
+    switch (a.K)
+    {
+        case 1: err = i8_launch<1>(stream, grid, L.total, p, tmap); break;
+        case 2: err = i8_launch<2>(stream, grid, L.total, p, tmap); break;
+        case 3: err = i8_launch<3>(stream, grid, L.total, p, tmap); break;
+        case 4: err = i8_launch<4>(stream, grid, L.total, p, tmap); break;
+        case 5: err = i8_launch<5>(stream, grid, L.total, p, tmap); break;
+        case 6: err = i8_launch<6>(stream, grid, L.total, p, tmap); break;
+        case 7: err = i8_launch<7>(stream, grid, L.total, p, tmap); break;
+        case 8: err = i8_launch<8>(stream, grid, L.total, p, tmap); break;
+    }
+    count_launch();
+    EXL3B_CUDA(err);
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return EXL3B_TAG_TC_I8;
+}
+
+bool mgemm_tc_i8_supported(const DevCtx* ctx, const MGemmArgs& a)
+{
+    // dense case only: one output per matrix, shared or per-matrix input, no routing / weighting / ragged widths
+    if (a.cb != 2 || a.m < 1 || a.m > I8_MAX_M) return false;
+    if (a.indices || a.weights || a.size_n_list || a.min_index >= 0 || a.num_tokens != 1) return false;
+    if (a.bszm_out < 1 || !(a.bszm_in == 1 || a.bszm_in == a.bszm_out)) return false;
+    if (a.bszm_out > ctx->num_sms || a.bszm_out > DevCtx::TMAP_SLOTS) return false;
+    if (a.k < 128 || a.n < 128 || a.k % 128 || a.n % 128) return false;
+    if ((long long) a.bszm_out * (a.n / 128) > DevCtx::COUNTERS_PER_SLOT) return false;
+    return true;
+}
+
+// exl3_mgemm, dense case, as ONE launch: the persistent grid is split into bszm_out groups of CTAs, one group per matrix.
+// Replaces exl3_mgemm_kernel for the reference's fused k+v and gate+up projections (modules/attn.py:603-631,
+// modules/mlp.py:726-760).  The weight tensor map is patched per CTA on the device (the pointer table is device memory).
+int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
+{
+    const int mats = a.bszm_out;
+    CUtensorMap tmap;
+    { int r = get_weight_tmap(ctx->ws, a.k, a.n, a.K, &tmap); if (r) return r; }     // template: address patched per CTA
+    const int slot = ctx->next_slot();
+    TcParams p{};
+    p.C = a.C; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
+    p.out_scale = 1.f; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
+    p.A_raw = a.A; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
+    p.num_mats = mats;                           // > 0 selects the table-driven path in the kernel
+    p.B_ptrs = a.B_ptrs; p.suh_ptrs = a.suh_ptrs; p.svh_ptrs = a.svh_ptrs;
+    p.a_mat_stride = a.bszm_in == 1 ? 0 : (long long) a.m * a.k;
+    p.c_mat_stride = (long long) a.m * a.n * (a.c_fp32 ? 4 : 2);
+    p.tmap_slots = ctx->tmap_slot(slot);
+    const int stage_bytes = 2048 * a.K + I8_B_STAGE;
+    int cache_bytes = a.m * a.k * 2;
+    cache_bytes = (cache_bytes + 127) / 128 * 128;
+    if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
+    int stages = (200 * 1024 - cache_bytes) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) stages = 2;
+    p.stages = stages; p.b_bytes = I8_B_STAGE; p.b_load_bytes = cache_bytes;
+    const TcSmemLayout L = i8_smem_layout(a.K, stages, cache_bytes);
+    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_mgemm (i8): shared-memory budget exceeded");
+    const long long U = (long long) (a.k / 128) * (a.n / 128);
+    int gpm = ctx->num_sms / mats;
+    if (gpm > U) gpm = (int) U;
+    p.g_per_mat = gpm;
+    const int grid = gpm * mats;
     cudaError_t err = cudaSuccess;
     switch (a.K)
     {

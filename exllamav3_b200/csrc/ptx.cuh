@@ -112,6 +112,19 @@ __device__ __forceinline__ void prefetch_tmap(const void* tmap)
     asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }
 
+// ---- device-side tensor-map patching (multi-matrix launches: one template, per-CTA global address) ----------------
+// smem_tmap: 128-byte aligned shared-memory copy of the template; gmem_tmap: this CTA's 128-byte slot in global memory.
+// Warp-collective (cp_fenceproxy is .sync.aligned).  After this the slot can be used by cp.async.bulk.tensor.
+__device__ __forceinline__ void tmap_patch_address(uint32_t smem_tmap, void* gmem_tmap, uint64_t new_addr, int lane)
+{
+    if (lane == 0)
+        asm volatile("tensormap.replace.tile.global_address.shared::cta.b1024.b64 [%0], %1;" :: "r"(smem_tmap), "l"(new_addr) : "memory");
+    __syncwarp();
+    asm volatile("tensormap.cp_fenceproxy.global.shared::cta.tensormap::generic.release.gpu.sync.aligned [%0], [%1], 128;"
+                 :: "l"(gmem_tmap), "r"(smem_tmap) : "memory");
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(gmem_tmap) : "memory");
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

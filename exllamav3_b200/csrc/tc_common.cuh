@@ -36,6 +36,13 @@ struct TcParams
     int tmem_cols;               // 256 or 512
     const half* A_raw;           // fused input transform (m <= 8): raw activations (m, k) and suh; null -> xh_tiled is used
     const half* suh;
+    // multi-matrix launch (exl3_mgemm, dense case): the grid is num_mats groups of g_per_mat CTAs, group j works on
+    // matrix j exactly like a single-matrix launch with g_per_mat CTAs.  num_mats == 0: single matrix, fields unused.
+    int num_mats, g_per_mat;
+    const uint64_t* B_ptrs; const uint64_t* suh_ptrs; const uint64_t* svh_ptrs;
+    long long a_mat_stride;      // elements between the inputs of consecutive matrices (0 = shared input)
+    long long c_mat_stride;      // bytes between the outputs of consecutive matrices
+    uint8_t* tmap_slots;         // one 128-byte tensor-map slot per CTA (global memory)
     int knob_;                   // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA
     unsigned long long* dbg;     // optional per-CTA timeline (16 x u64 per CTA), bring-up only
 };

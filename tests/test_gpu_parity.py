@@ -317,6 +317,50 @@ def test_gemm_i8_tensor_core_path(cuda, K, m):
         ext.set_gemm_path(prev)
 
 
+@pytest.mark.parametrize("nm,per_mat_input", [(2, False), (2, True), (3, False), (7, False)])
+def test_mgemm_i8_tensor_core_single_launch(cuda, nm, per_mat_input):
+    """
+    Dense exl3_mgemm (the reference's fused k+v / gate+up call, modules/attn.py:603-631, modules/mlp.py:726-760) on the
+    mul1 int8 tensor-core path: ONE launch (tag 210), CTA groups per matrix, per-CTA patched tensor maps.  Each
+    matrix's output must equal the single-matrix i8 kernel bit for bit when the CTA group size matches, and must
+    meet the exl3_gemm tolerances against the fp64 oracle in every case.
+    """
+    from exllamav3_b200 import ext
+    prev = ext.set_gemm_path(0)
+    try:
+        for (k, n, K, m) in ((512, 384, 4, 1), (1024, 256, 3, 4), (256, 1152, 5, 2)):
+            mats = [orc.make_synthetic(k, n, K, seed=77 + 13 * e, m=m) for e in range(nm)]
+            rng = np.random.default_rng(nm * 100 + m)
+            A = rng.standard_normal((nm if per_mat_input else 1, m, k)).astype(np.float16)
+            trs = [T(t[0], cuda) for t in mats]; suhs = [T(t[1], cuda) for t in mats]; svhs = [T(t[2], cuda) for t in mats]
+            pt = torch.tensor([t.data_ptr() for t in trs], dtype=torch.long, device=cuda)
+            ps = torch.tensor([t.data_ptr() for t in suhs], dtype=torch.long, device=cuda)
+            pv = torch.tensor([t.data_ptr() for t in svhs], dtype=torch.long, device=cuda)
+            for fp32 in (True, False):
+                C = torch.full((nm, m, n), float("nan"), dtype=torch.float if fp32 else torch.half, device=cuda)
+                Ah = torch.empty((nm, m, k), dtype=torch.half, device=cuda)
+                before = ext.launch_count()
+                tag = ext.exl3_mgemm(T(A, cuda), pt, C, ps, Ah, pv, None, None, K, -1, False, True, -1, -1, 0)
+                assert tag == ext.EXL3B_TAG_TC_I8
+                assert ext.launch_count() - before == 1
+                Cn = C.float().cpu().numpy()
+                assert np.isfinite(Cn).all()
+                for j in range(nm):
+                    a = A[j] if per_mat_input else A[0]
+                    ref = orc.exl3_gemm_f64(a, mats[j][0], mats[j][1], mats[j][2], K, 2)
+                    mx, rms = rel_err(Cn[j], ref)
+                    assert mx <= 2e-3 + (2.0 ** -10 if not fp32 else 0) and rms <= 1e-3, (nm, k, n, K, m, j, fp32, mx, rms)
+                    model = orc.exl3_gemm_i8_model(a, mats[j][0], mats[j][1], mats[j][2], K)
+                    mx, rms = rel_err(Cn[j], model)
+                    assert mx <= (2e-5 if fp32 else 1.5e-3), (nm, k, n, K, m, j, fp32, mx)
+                # repeated launches are bit-identical (fixed-order split-K inside every CTA group)
+                C2 = torch.empty_like(C)
+                ext.exl3_mgemm(T(A, cuda), pt, C2, ps, Ah, pv, None, None, K, -1, False, True, -1, -1, 0)
+                assert torch.equal(C, C2)
+    finally:
+        ext.set_gemm_path(prev)
+
+
 def test_tc_determinism_and_stream_k(cuda):
     """Split-K partials are combined in a fixed order: repeated launches are bit-identical; shapes chosen so that
     strips are split across CTAs (k large, n small) and so that CTAs span several strips (n large)."""
