@@ -97,7 +97,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     auto stamp = [&](int slot)
     {
 #ifdef EXL3B_TC_DEBUG
-        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[blockIdx.x * 64 + slot] = t; }
+        if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); p.dbg[blockIdx.x * 64 + slot] = t; }
 #else
         (void) slot;
 #endif
@@ -211,7 +211,13 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         const uint32_t idesc = idesc_u8s8_s32(128, I8_NT);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t x_smem0 = smem_u32(smem + L.off_b);
-        const uint64_t desc_hi = smem_desc(0, 128, 4096, 0);       // K-adjacent core matrices 128 B apart, row groups 4096 B
+        // descriptor: K-adjacent core matrices 128 B apart (LBO), row groups 4096 B (SBO); only the 14-bit start address
+        // (16-byte units) changes: + b_bytes / 16 per stage, + 16 per MMA (256 B = 32 K-bytes x 8 rows)
+        const uint64_t desc0 = smem_desc(x_smem0, 128, 4096, 0);
+        const uint32_t desc_hi = (uint32_t) (desc0 >> 32);
+        const uint32_t desc_lo0 = (uint32_t) desc0;
+        const uint32_t desc_step = (uint32_t) (L.b_bytes >> 4);
+        uint32_t desc_lo = desc_lo0;
         int dbuf = 0, dphase = 0, seg_left = 0, sub_left = 0;
         uint32_t acc = 0;
         int tsum = 0;                                              // lane r < m: digit sum of row r over the sub-segment
@@ -231,13 +237,22 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 acc = 0;
                 tsum = 0;
             }
+#ifdef EXL3B_TC_DEBUG
+            const bool mst = lane == 0 && u >= 8 && u < 12 && p.dbg;
+            if (mst) stamp(32 + 4 * (u - 8));
+#endif
             mbar_wait(X_FULL(s), sph);
+#ifdef EXL3B_TC_DEBUG
+            if (mst) stamp(33 + 4 * (u - 8));
+#endif
             mbar_wait(A_FULL(as), aph);
             tc_fence_after();
+#ifdef EXL3B_TC_DEBUG
+            if (mst) stamp(34 + 4 * (u - 8));
+#endif
             if (lane < p.m) tsum += *reinterpret_cast<const int*>(smem + L.off_b + s * L.b_bytes + I8_B_BYTES + 4 * lane);
             const uint32_t d_addr = tb + I8_D_COL0 + dbuf * I8_NT;
             const uint32_t a_addr = tb + as * I8_A_STAGE_COLS;
-            const uint32_t b_addr = x_smem0 + s * L.b_bytes;
             --seg_left; --sub_left;
             if (sub_left == 0)
             {
@@ -251,7 +266,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                 {
-                    mma_i8_ts(d_addr, a_addr + 8 * j, desc_hi | (uint64_t) (((b_addr + j * 256) >> 4) & 0x3fff), idesc, acc);
+                    mma_i8_ts_lohi(d_addr, a_addr + 8 * j, desc_lo + 16 * j, desc_hi, idesc, acc);
                     acc = 1;
                 }
                 tc_commit(A_EMPTY(as));
@@ -260,9 +275,13 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             }
             acc = 1;
             __syncwarp();
+#ifdef EXL3B_TC_DEBUG
+            if (mst) stamp(35 + 4 * (u - 8));
+#endif
             if (sub_left == 0) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
             if (++kb == KB) kb = 0;
-            if (++s == S) { s = 0; sph ^= 1; }
+            desc_lo += desc_step;
+            if (++s == S) { s = 0; sph ^= 1; desc_lo = desc_lo0; }
             if (++as == I8_A_STAGES) { as = 0; aph ^= 1; }
         }
         __syncwarp();
@@ -338,13 +357,24 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         int s = g % S, sph = 0, as = g % I8_A_STAGES, aph = 0;
         for (int u = g; u < n_units; u += I8_DEC_GROUPS)
         {
+#ifdef EXL3B_TC_DEBUG
+            const bool st_on = warp == TC_DEC_WARP0 && lane == 0 && (u == 8 || u == 10) && p.dbg;
+            const int st0 = 16 + (u == 10 ? 8 : 0);
+#define I8_STAMP(i) if (st_on) stamp(st0 + (i))
+#else
+#define I8_STAMP(i)
+#endif
+            I8_STAMP(0);
             mbar_wait<32>(W_FULL(s), sph);
+            I8_STAMP(1);
             if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
             const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
             uint32_t w[4][K + 1];
             tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub+2, sub+4, sub+6
+            I8_STAMP(2);
             mbar_wait(A_EMPTY(as), aph ^ 1);
             tc_fence_after();
+            I8_STAMP(3);
             #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
@@ -360,10 +390,13 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                     tmem_st_32x32b_x16(tmem_base + lane_base + as * I8_A_STAGE_COLS + 16 * t, o);
                 else if (o[0] == 0x12345678u && o[15] == 0x9abcdef0u) p.counters[0] = 1;
             }
+            I8_STAMP(4);
             tc_wait_st();
+            I8_STAMP(5);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
+            I8_STAMP(6);
             if (warp == TC_DEC_WARP0 && lane == 0 && u == 0) stamp(4);
             if (q == 0 && sub == 0 && lane == 0 && u == n_units - 1) stamp(10);
             s += I8_DEC_GROUPS; if (s >= S) { s -= S; sph ^= 1; }

@@ -177,6 +177,17 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, the shared-memory descriptor given as its two 32-bit halves (lets the caller step the 14-bit start-address field
+// with one 32-bit add per instruction instead of rebuilding the 64-bit descriptor)
+__device__ __forceinline__ void mma_i8_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 bd, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"

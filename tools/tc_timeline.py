@@ -47,6 +47,21 @@ for i, d in enumerate(D):
         if len(v):
             print(f"  {names[s]:28s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
 
+# int8 kernel: decode warp 4 at units 8 and 10, MMA warp at units 8..11
+d = D[3]
+if path == 210 and (d[:, 16] > 0).any():
+    lab = ["loop top", "W_FULL", "LDS+SHFL", "A_EMPTY", "decode+STTM issued", "wait::st", "arrived"]
+    base = d[:, 16]
+    ok = base > 0
+    for uu in range(2):
+        row = [int(np.median((d[:, 16 + uu * 8 + i] - base)[ok & (d[:, 16 + uu * 8 + i] > 0)])) for i in range(7)]
+        print("  i8 decode warp, unit", 8 + 2 * uu, dict(zip(lab, row)))
+    labm = ["loop top", "X_FULL", "A_FULL", "issued+committed"]
+    for uu in range(4):
+        row = [int(np.median((d[:, 32 + uu * 4 + i] - base)[ok & (d[:, 32 + uu * 4 + i] > 0)])) for i in range(4)]
+        print("  i8 mma warp, unit", 8 + uu, dict(zip(labm, row)))
+    sys.exit(0)
+
 # fine-grained decode-warp stamps (exact kernel only): units 8..11 of each CTA, warp 4 lane 0
 d = D[3]
 if (d[:, 16] > 0).any():
