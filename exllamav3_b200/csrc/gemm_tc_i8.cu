@@ -102,6 +102,13 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         (void) slot;
 #endif
     };
+#ifdef EXL3B_TC_DEBUG
+    // how often did a role find its barrier not yet complete (= it had to wait)?  slots 56.. of the CTA's debug row
+    int wf_a = 0, wf_b = 0, wf_c = 0;
+#define I8_WAITCNT(cnt, bar, par) do { if (!mbar_test_wait((bar), (par))) ++(cnt); } while (0)
+#else
+#define I8_WAITCNT(cnt, bar, par) do { } while (0)
+#endif
     if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
@@ -194,7 +201,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         int s = 0, ph = 0;
         for (int u = 0; u < n_units; ++u)
         {
-            if (u >= S) mbar_wait<64>(W_EMPTY(s), ph ^ 1);
+            if (u >= S) { I8_WAITCNT(wf_a, W_EMPTY(s), ph ^ 1); mbar_wait<64>(W_EMPTY(s), ph ^ 1); }
             if (elect_one())
             {
                 mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
@@ -204,6 +211,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (++s == S) { s = 0; ph ^= 1; }
         }
         __syncwarp();
+#ifdef EXL3B_TC_DEBUG
+        if (lane == 0 && p.dbg) p.dbg[blockIdx.x * 64 + 56] = wf_a;
+#endif
     }
     else if (warp == 1)
     {
@@ -220,7 +230,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         uint32_t desc_lo = desc_lo0;
         int dbuf = 0, dphase = 0, seg_left = 0, sub_left = 0;
         uint32_t acc = 0;
-        int tsum = 0;                                              // lane r < m: digit sum of row r over the sub-segment
+        int tsum = 0, tload = 0;                                   // lane r < m: digit sum of row r over the sub-segment
         int kb = (int) (ubeg % KB);
         int s = 0, sph = 0, as = 0, aph = 0;
         for (int u = 0; u < n_units; ++u)
@@ -235,27 +245,28 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 sub_left = seg_left < I8_SUB_UNITS ? seg_left : I8_SUB_UNITS;
                 mbar_wait(D_EMPTY(dbuf), dphase ^ 1);
                 acc = 0;
-                tsum = 0;
+                tsum = 0; tload = 0;
             }
 #ifdef EXL3B_TC_DEBUG
             const bool mst = lane == 0 && u >= 8 && u < 12 && p.dbg;
             if (mst) stamp(32 + 4 * (u - 8));
 #endif
-            mbar_wait(X_FULL(s), sph);
-#ifdef EXL3B_TC_DEBUG
-            if (mst) stamp(33 + 4 * (u - 8));
-#endif
+            // (the activation digits of this unit are complete too: the decode group's lead warp waited for X_FULL
+            // before it arrived here -- one barrier round trip less on this warp's serial path)
+            I8_WAITCNT(wf_b, A_FULL(as), aph);
             mbar_wait(A_FULL(as), aph);
             tc_fence_after();
 #ifdef EXL3B_TC_DEBUG
             if (mst) stamp(34 + 4 * (u - 8));
 #endif
-            if (lane < p.m) tsum += *reinterpret_cast<const int*>(smem + L.off_b + s * L.b_bytes + I8_B_BYTES + 4 * lane);
+            tsum += tload;                                              // previous unit's load: consumed one iteration late
+            if (lane < p.m) tload = *reinterpret_cast<const int*>(smem + L.off_b + s * L.b_bytes + I8_B_BYTES + 4 * lane);
             const uint32_t d_addr = tb + I8_D_COL0 + dbuf * I8_NT;
-            const uint32_t a_addr = tb + as * I8_A_STAGE_COLS;
+            uint32_t a_addr = tb + as * I8_A_STAGE_COLS;
             --seg_left; --sub_left;
             if (sub_left == 0)
             {
+                tsum += tload; tload = 0;
                 if (lane < p.m) s_tout[dbuf * I8_MAX_M + lane] = tsum;      // visible to the epilogue before D_FULL fires
                 __threadfence_block();
                 __syncwarp();
@@ -263,11 +274,14 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (elect_one())
             {
                 if (!(KNOB & 4))
-                #pragma unroll
-                for (int j = 0; j < 16; ++j)
                 {
-                    mma_i8_ts_lohi(d_addr, a_addr + 8 * j, desc_lo + 16 * j, desc_hi, idesc, acc);
-                    acc = 1;
+                    uint32_t dl = desc_lo;
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                    {
+                        mma_i8_ts_step<8, 16>(d_addr, a_addr, dl, desc_hi, idesc, acc);
+                        acc = 1;
+                    }
                 }
                 tc_commit(A_EMPTY(as));
                 tc_commit(W_EMPTY(s));
@@ -285,6 +299,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (++as == I8_A_STAGES) { as = 0; aph ^= 1; }
         }
         __syncwarp();
+#ifdef EXL3B_TC_DEBUG
+        if (lane == 0 && p.dbg) { p.dbg[blockIdx.x * 64 + 57] = wf_a; p.dbg[blockIdx.x * 64 + 58] = wf_b; }
+#endif
     }
     else if (warp < TC_DEC_WARP0)
     {
@@ -302,6 +319,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         const int kstep = 2 % KB;
         for (int u = xw; u < n_units; u += 2)
         {
+            I8_WAITCNT(wf_a, W_EMPTY(s), ph ^ 1);
             mbar_wait<64>(W_EMPTY(s), ph ^ 1);
             uint8_t* dst = smem + L.off_b + s * L.b_bytes;
             #pragma unroll
@@ -343,6 +361,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             kb += kstep; if (kb >= KB) kb -= KB;
             s += 2; if (s >= S) { s -= S; ph ^= 1; }
         }
+#ifdef EXL3B_TC_DEBUG
+        if (xw == 0 && lane == 0 && p.dbg) p.dbg[blockIdx.x * 64 + 61] = wf_a;
+#endif
     }
     else if (warp < TC_EPI_WARP0)
     {
@@ -365,6 +386,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 #define I8_STAMP(i)
 #endif
             I8_STAMP(0);
+            I8_WAITCNT(wf_a, W_FULL(s), sph);
             mbar_wait<32>(W_FULL(s), sph);
             I8_STAMP(1);
             if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
@@ -372,6 +394,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             uint32_t w[4][K + 1];
             tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub+2, sub+4, sub+6
             I8_STAMP(2);
+            I8_WAITCNT(wf_b, A_EMPTY(as), aph ^ 1);
             mbar_wait(A_EMPTY(as), aph ^ 1);
             tc_fence_after();
             I8_STAMP(3);
@@ -394,6 +417,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             tc_wait_st();
             I8_STAMP(5);
             tc_fence_before();
+            if (sub == 0 && q == 0) mbar_wait(X_FULL(s), sph);      // lead warp of the group vouches for the activation digits
             __syncwarp();
             if (lane == 0) { mbar_arrive(A_FULL(as)); mbar_arrive(W_EMPTY(s)); }
             I8_STAMP(6);
@@ -402,6 +426,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             s += I8_DEC_GROUPS; if (s >= S) { s -= S; sph ^= 1; }
             as += I8_DEC_GROUPS; if (as >= I8_A_STAGES) { as -= I8_A_STAGES; aph ^= 1; }
         }
+#ifdef EXL3B_TC_DEBUG
+        if (warp == TC_DEC_WARP0 && lane == 0 && p.dbg) { p.dbg[blockIdx.x * 64 + 59] = wf_a; p.dbg[blockIdx.x * 64 + 60] = wf_b; }
+#endif
     }
     else
     {

@@ -51,6 +51,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
+// non-blocking probe (diagnostics only)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall-clock
 // (%globaltimer, checked every 1024 polls), not an iteration count: try_wait returns early whenever ANY barrier
 // activity wakes the warp, so iteration counts say nothing about elapsed time.
@@ -187,6 +197,20 @@ __device__ __forceinline__ void mma_i8_ts_lohi(uint32_t d_tmem, uint32_t a_tmem,
                  "mov.b64 bd, {%2, %3};\n\t"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, stepping the A address and the descriptor start address in place after the issue (keeps the whole unrolled MMA
+// sequence on ONE uniform-register pair instead of one pair + one high-word move per instruction)
+template <int A_STEP, int B_STEP>
+__device__ __forceinline__ void mma_i8_ts_step(uint32_t d_tmem, uint32_t& a_tmem, uint32_t& b_desc_lo, uint32_t b_desc_hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 bd, {%1, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%2], [%0], bd, %4, p;\n\t"
+                 "add.u32 %0, %0, %6;\n\t"
+                 "add.u32 %1, %1, %7;\n\t}"
+                 : "+r"(a_tmem), "+r"(b_desc_lo) : "r"(d_tmem), "r"(b_desc_hi), "r"(idesc), "r"(accumulate), "n"(A_STEP), "n"(B_STEP) : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16])
 {

@@ -56,6 +56,10 @@ if path == 210 and (d[:, 16] > 0).any():
     for uu in range(2):
         row = [int(np.median((d[:, 16 + uu * 8 + i] - base)[ok & (d[:, 16 + uu * 8 + i] > 0)])) for i in range(7)]
         print("  i8 decode warp, unit", 8 + 2 * uu, dict(zip(lab, row)))
+    units = (k // 128) * (n // 128) / 148
+    wl = {56: "producer W_EMPTY", 57: "mma X_FULL", 58: "mma A_FULL", 59: "decode(g0) W_FULL", 60: "decode(g0) A_EMPTY", 61: "xf(w0) W_EMPTY"}
+    print(f"  waits that found the barrier incomplete, median per CTA ({units:.1f} units/CTA; decode group / xf warp see half):",
+          {v: int(np.median(d[:, s_][ok])) for s_, v in wl.items()})
     labm = ["loop top", "X_FULL", "A_FULL", "issued+committed"]
     for uu in range(4):
         row = [int(np.median((d[:, 32 + uu * 4 + i] - base)[ok & (d[:, 32 + uu * 4 + i] > 0)])) for i in range(4)]
