@@ -12,7 +12,7 @@ dev = torch.device("cuda:0")
 path = int(os.environ.get("EXL3B_PATH", "210"))
 ext.set_gemm_path(path)
 shapes = [(4096, 128256, 6, 2), (4096, 14336, 4, 8), (4096, 4096, 4, 24), (14336, 4096, 4, 8)]
-knobs = [0, 1, 3, 4, 7, 8, 15]
+knobs = [int(v) for v in os.environ.get('KNOBS', '0,1,3,4,7,8,15').split(',')]
 for (k, n, K, copies) in shapes:
     g = torch.Generator(device=dev); g.manual_seed(1)
     trs = [torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16) for _ in range(copies)]
