@@ -55,6 +55,8 @@ int get_ctx(DevCtx** out)
         EXL3B_CUDA(cudaMemset(c.counters, 0, sizeof(int) * DevCtx::NUM_SLOTS * DevCtx::COUNTERS_PER_SLOT));
         EXL3B_CUDA(cudaMalloc(&c.tabs, sizeof(MSlotTable) * DevCtx::NUM_SLOTS));
         EXL3B_CUDA(cudaMalloc(&c.tmap_slots, (size_t) DevCtx::NUM_SLOTS * DevCtx::TMAP_SLOTS * 128));
+        EXL3B_CUDA(cudaMalloc(&c.i8_parts, (size_t) DevCtx::NUM_SLOTS * DevCtx::I8_PART_CTAS * 512 * sizeof(float)));
+        EXL3B_CUDA(cudaMemset(c.i8_parts, 0xff, (size_t) DevCtx::NUM_SLOTS * DevCtx::I8_PART_CTAS * 512 * sizeof(float)));
         EXL3B_CUDA(cudaDeviceSynchronize());
         c.device = dev;
     }

@@ -36,6 +36,7 @@ constexpr int I8_NT = 16;                                      // N: rows 2r = h
 constexpr int I8_B_BYTES = 4096;                               // one row group: 32 K-chunks x (8 rows x 16 B)
 constexpr int I8_B_STAGE = I8_B_BYTES + 64;                    // + per-row digit sums of the unit
 constexpr int I8_SUB_UNITS = 96;                               // int32 accumulator safety: <= 12288 k per accumulation
+constexpr uint32_t I8_SENTINEL = 0xffffffffu;                  // "no partial sum here yet" in the split-K exchange buffer
 constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 256 + 0  -> hi in [-127, 127]
 
 // optional shared-memory cache of the whole transformed activation (m x k fp16) and of the per-block digit sums, filled by
@@ -67,9 +68,11 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const half* suh = p.suh; const half* svh = p.svh; const half* A_raw = p.A_raw;
     char* Cout = (char*) p.C; float* ws = p.ws; int* counters = p.counters;
     const bool multi = p.num_mats > 0;
+    float* const parts = p.parts;                    // split-K exchange buffer, one slot of I8_MAX_M x 128 floats per CTA of the grid
+    int cta0 = 0;                                    // first CTA of this matrix's group
     if (multi)
     {
-        G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G;
+        G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G;
         suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
         A_raw += (size_t) mat * p.a_mat_stride; Cout += (size_t) mat * p.c_mat_stride;
         ws += (size_t) mat * 2 * G * (I8_MAX_M * 128); counters += mat * (p.n / 128);
@@ -469,7 +472,6 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + KB - 1);
             const int n_contrib = c_b - c_a + 1;
             const bool full = n_contrib == 1;
-            float* my_part = ws + (size_t) (2 * cta + (ubeg >= gs ? 0 : 1)) * part_stride;
 
             float facc[I8_MAX_M];
             #pragma unroll
@@ -509,55 +511,79 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) tile[r * 128 + col] = facc[r];
                 emit_rows(strip);
             }
+            else if (cta != c_a)
+            {
+                // Contributor: publish the partial sums and move on.  The data is its own flag: the exchange buffer holds the
+                // sentinel everywhere outside a launch, a 32-bit store is single-copy atomic, so no fence, counter or ticket.
+                #pragma unroll
+                for (int r = 0; r < I8_MAX_M; ++r)
+                    if (r < p.m)
+                    {
+                        uint32_t bits = __float_as_uint(facc[r]);
+                        if (bits == I8_SENTINEL) bits = 0x7fc00000u;                 // a NaN stays a NaN
+                        st_relaxed_gpu_u32(reinterpret_cast<uint32_t*>(parts + (size_t) (cta0 + cta) * part_stride + r * 128 + col), bits);
+                    }
+                if (et == 0 && u + seg >= n_units) stamp(11);
+            }
             else
             {
+                // The CTA that owns the strip's FIRST k-segment works on it LAST (segments are processed in unit order), so it is the
+                // natural reducer: own sums from registers, then the others' in fixed CTA order (bit-reproducible).  One global
+                // round trip in the common case -- the old protocol needed three (fence + ticket, then the loads).
                 #pragma unroll
-                for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) my_part[r * 128 + col] = facc[r];
-                epi_bar();                                    // all partial stores of this CTA are ordered before ...
-                if (et == 0 && u + seg >= n_units) stamp(11);
-                if (et == 0)
+                for (int r = 0; r < I8_MAX_M; ++r)
                 {
-                    __threadfence();                          // ... this single gpu-scope fence + the arrival count (cumulativity)
-                    const int old = atomicAdd(&counters[strip], 1);
-                    const int last = old == n_contrib - 1;
-                    if (last) { counters[strip] = 0; __threadfence(); }
-                    *s_flag = last;
-                }
-                epi_bar();
-                if (et == 0 && u + seg >= n_units) stamp(12);
-                if (*s_flag)
-                {
-                    // contributors c_a..c_b in fixed order (deterministic); slot = 2c + (first segment of c ? 0 : 1).
-                    // Only c_a can have started in an earlier strip.  All loads are issued before the first add.
-                    #pragma unroll
-                    for (int r = 0; r < I8_MAX_M; ++r)
+                    if (r < p.m)
                     {
-                        if (r < p.m)
+                        float a = 0.f;
+                        a += facc[r];
+                        int c = c_a + 1;
+                        while (c <= c_b)
                         {
-                            float a = 0.f;
-                            const int which_a = unit_begin(U, G, c_a) >= gs ? 0 : 1;
-                            int c = c_a;
-                            while (c <= c_b)
+                            uint32_t v[8];
+                            bool ok;
+                            uint32_t polls = 0;
+                            unsigned long long t0 = 0;
+                            do
                             {
-                                float v[8];
+                                ok = true;
                                 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                 {
                                     const int cc = c + j;
-                                    const int which = cc == c_a ? which_a : 0;
-                                    v[j] = cc <= c_b ? __ldcg(ws + (size_t) (2 * cc + which) * part_stride + r * 128 + col) : 0.f;
+                                    v[j] = 0u;
+                                    if (cc <= c_b)
+                                    {
+                                        v[j] = ld_relaxed_gpu_u32(reinterpret_cast<const uint32_t*>(parts + (size_t) (cta0 + cc) * part_stride + r * 128 + col));
+                                        ok = ok && v[j] != I8_SENTINEL;
+                                    }
                                 }
-                                #pragma unroll
-                                for (int j = 0; j < 8; ++j) a += v[j];
-                                c += 8;
+                                if (!ok && (++polls & 255u) == 0)
+                                {
+                                    unsigned long long t;
+                                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                                    if (t0 == 0) t0 = t;
+                                    else if (t - t0 > 4000000000ull) { printf("exl3b: split-K exchange timeout (block %d strip %d)\n", blockIdx.x, strip); __trap(); }
+                                }
+                            } while (!ok);
+                            #pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                            {
+                                const int cc = c + j;
+                                if (cc <= c_b)
+                                {
+                                    a += __uint_as_float(v[j]);
+                                    // re-arm the slot for the launch that uses this exchange buffer next (8 launches from now)
+                                    st_relaxed_gpu_u32(reinterpret_cast<uint32_t*>(parts + (size_t) (cta0 + cc) * part_stride + r * 128 + col), I8_SENTINEL);
+                                }
                             }
-                            tile[r * 128 + col] = a;
+                            c += 8;
                         }
+                        tile[r * 128 + col] = a;
                     }
-                    if (et == 0 && u + seg >= n_units) stamp(13);
-                    emit_rows(strip);
                 }
-                epi_bar();
+                if (et == 0 && u + seg >= n_units) stamp(13);
+                emit_rows(strip);
             }
             u += seg;
         }
@@ -609,6 +635,7 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     p.B = a.B; p.C = a.C; p.svh = a.svh; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
     p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
+    p.parts = ctx->i8_parts_slot(slot);
     const int stage_bytes = 2048 * a.K + I8_B_STAGE;
     int cache_bytes = a.m * a.k * 2;
     cache_bytes = (cache_bytes + 127) / 128 * 128;
@@ -672,6 +699,7 @@ int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
     p.a_mat_stride = a.bszm_in == 1 ? 0 : (long long) a.m * a.k;
     p.c_mat_stride = (long long) a.m * a.n * (a.c_fp32 ? 4 : 2);
     p.tmap_slots = ctx->tmap_slot(slot);
+    p.parts = ctx->i8_parts_slot(slot);
     const int stage_bytes = 2048 * a.K + I8_B_STAGE;
     int cache_bytes = a.m * a.k * 2;
     cache_bytes = (cache_bytes + 127) / 128 * 128;

@@ -135,6 +135,18 @@ __device__ __forceinline__ void tmap_patch_address(uint32_t smem_tmap, void* gme
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(gmem_tmap) : "memory");
 }
 
+// ---- relaxed gpu-scope accesses (flag-in-data exchange through L2) ------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

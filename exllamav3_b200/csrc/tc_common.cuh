@@ -42,6 +42,7 @@ struct TcParams
     const uint64_t* B_ptrs; const uint64_t* suh_ptrs; const uint64_t* svh_ptrs;
     long long a_mat_stride;      // elements between the inputs of consecutive matrices (0 = shared input)
     long long c_mat_stride;      // bytes between the outputs of consecutive matrices
+    float* parts;                // i8 path: sentinel-managed split-K exchange buffer (one 4 x 128 fp32 slot per CTA)
     uint8_t* tmap_slots;         // one 128-byte tensor-map slot per CTA (global memory)
     int knob_;                   // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA
     unsigned long long* dbg;     // optional per-CTA timeline (16 x u64 per CTA), bring-up only
