@@ -102,11 +102,12 @@ gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
-    if (threadIdx.x == 0)
+    if (warp == 0)
     {
-        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / TC_DEC_GROUPS + 1); }
-        for (int s = 0; s < 8; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS / TC_DEC_GROUPS); mbar_init(A_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
+        // one barrier per lane and round instead of ~70 serial initialisations by one thread
+        for (int s = lane; s < S; s += 32) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / TC_DEC_GROUPS + 1); }
+        if (lane < 8) { mbar_init(A_FULL(lane), TC_DEC_WARPS / TC_DEC_GROUPS); mbar_init(A_EMPTY(lane), 1); }
+        else if (lane < 10) { mbar_init(D_FULL(lane - 8), 1); mbar_init(D_EMPTY(lane - 8), 4); }
         fence_barrier_init();
     }
     if (warp == 1)

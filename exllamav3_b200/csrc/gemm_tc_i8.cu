@@ -115,12 +115,13 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     if (threadIdx.x == 0) stamp(0);
     pdl_launch_dependents();
 
-    if (threadIdx.x == 0)
+    if (warp == 0)
     {
-        for (int s = 0; s < S; ++s) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / I8_DEC_GROUPS + 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(A_FULL(s), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(D_FULL(s), 1); mbar_init(D_EMPTY(s), 4); }
-        for (int r = 0; r < I8_MAX_M; ++r) s_absmax[r] = 0u;
+        // one barrier per lane and round instead of ~60 serial initialisations by one thread (0.3 us of every launch)
+        for (int s = lane; s < S; s += 32) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / I8_DEC_GROUPS + 1); }
+        if (lane < 4) { mbar_init(A_FULL(lane), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(lane), 1); }
+        else if (lane < 6) { mbar_init(D_FULL(lane - 4), 1); mbar_init(D_EMPTY(lane - 4), 4); }
+        else if (lane < 6 + I8_MAX_M) s_absmax[lane - 6] = 0u;
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
