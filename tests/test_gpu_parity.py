@@ -382,6 +382,57 @@ def test_tc_determinism_and_stream_k(cuda):
         ext.set_gemm_path(prev)
 
 
+def test_i8_split_k_exchange_ring(cuda):
+    """
+    The int8 path exchanges split-K partial sums through a buffer that must be all-sentinel between launches (contributors
+    store, the strip's reducer reads and re-arms; 8 rotating slot sets).  Interleave shapes with different grids, strip
+    splits and row counts -- single-matrix and multi-matrix launches, back to back without host synchronisation, several
+    times around the slot ring -- and require every result to stay bit-identical to its first computation: a slot left
+    un-armed (or armed too early) would be consumed as a stale partial sum by a later launch.
+    """
+    from exllamav3_b200 import ext
+    prev = ext.set_gemm_path(0)
+    try:
+        cases = []
+        for (k, n, m) in ((16384, 128, 1), (4096, 256, 3), (2048, 1024, 4), (8192, 384, 2), (128, 2048, 1)):
+            tr, suh, svh, x = orc.make_synthetic(k, n, 4, m=m)
+            cases.append(dict(k=k, n=n, m=m, x=T(x, cuda), tr=T(tr, cuda), suh=T(suh, cuda), svh=T(svh, cuda),
+                              xh=torch.empty((m, k), dtype=torch.half, device=cuda), ref=orc.exl3_gemm_f64(x, tr, suh, svh, 4, 2)))
+        # one multi-matrix case (two matrices sharing the input)
+        k, n, m = 4096, 512, 2
+        mats = [orc.make_synthetic(k, n, 4, seed=900 + e, m=m) for e in range(2)]
+        trs = [T(t[0], cuda) for t in mats]; suhs = [T(t[1], cuda) for t in mats]; svhs = [T(t[2], cuda) for t in mats]
+        ptr = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.long, device=cuda)
+        mg = dict(x=T(mats[0][3], cuda).view(1, m, k), B=ptr(trs), suh=ptr(suhs), svh=ptr(svhs),
+                  xh=torch.empty((2, m, k), dtype=torch.half, device=cuda))
+        first = {}
+        for rnd in range(6):                                   # 6 x 6 launches = 4.5 times around the 8-deep ring
+            outs = []
+            for i, c in enumerate(cases):
+                y = torch.empty((c["m"], c["n"]), dtype=torch.float, device=cuda)
+                tag = ext.exl3_gemm(c["x"], c["tr"], y, c["suh"], c["xh"], c["svh"], -1, False, True, 0)
+                assert tag == ext.EXL3B_TAG_TC_I8
+                outs.append((i, y))
+            y2 = torch.empty((2, m, n), dtype=torch.float, device=cuda)
+            assert ext.exl3_mgemm(mg["x"], mg["B"], y2, mg["suh"], mg["xh"], mg["svh"], None, None, 4, -1, False, True, -1, -1, 0) == ext.EXL3B_TAG_TC_I8
+            outs.append(("mg", y2))
+            torch.cuda.synchronize()
+            for key, y in outs:
+                if key not in first:
+                    first[key] = y.clone()
+                else:
+                    assert torch.equal(first[key], y), (rnd, key)
+        for i, c in enumerate(cases):
+            mx, rms = rel_err(first[i].cpu().numpy(), c["ref"])
+            assert mx <= 2e-3 and rms <= 1e-3, (c["k"], c["n"], c["m"], mx, rms)
+        for j in range(2):
+            ref = orc.exl3_gemm_f64(mats[0][3], mats[j][0], mats[j][1], mats[j][2], 4, 2)
+            mx, rms = rel_err(first["mg"][j].cpu().numpy(), ref)
+            assert mx <= 2e-3 and rms <= 1e-3, (j, mx, rms)
+    finally:
+        ext.set_gemm_path(prev)
+
+
 def test_full_size_properties(cuda):
     """
     BASELINE.json sizes (Llama-3.1-8B shapes, K=4, mul1) where the numpy oracle is too slow for a dense check:
