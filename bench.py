@@ -178,6 +178,7 @@ class Token:
         import torch
         from exllamav3_b200 import ext
         self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
+        self.skip_reduce = False
         g = torch.Generator(device=dev); g.manual_seed(seed + rank)
         layer, head = token_plan(cfg, tp)
         self.mats = []
@@ -221,7 +222,7 @@ class Token:
             if ln["kind"] == "gemm":
                 mt = ln["mt"]
                 ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
-                if mt["reduce"]:
+                if mt["reduce"] and not self.skip_reduce:
                     import torch.distributed as dist
                     dist.all_reduce(mt["y"])
             else:
@@ -244,7 +245,10 @@ def run_gpu_arm(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     from exllamav3_b200 import ext
 
-    tok = Token(cfg, world, rank, dev, fuse=not args.no_fuse)
+    tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse)
+    if args.tp_shapes:
+        # single-GPU dry run of ONE rank's shard of a TP-N token (kernel shapes only, no collective): not a bench result
+        tok.skip_reduce = True
     stream = torch.cuda.Stream(device=dev)
     launches0 = ext.launch_count()
     with torch.cuda.stream(stream):
@@ -358,7 +362,7 @@ def run_gpu_arm(args, cfg):
                                    f"{len(tok.mats)} quantized matrices/token in {len(tok.launches)} launches "
                                    f"(k+v and gate+up as exl3_mgemm like the reference's decode path), m=1, mul1 codebook, "
                                    f"random-init trellis",
-                       "parallelism": f"tp{world}" if world > 1 else "single",
+                       "parallelism": (f"tp{world}" if world > 1 else "single") + (f" (DRY RUN of tp{args.tp_shapes} rank-0 shapes, no collective: not a result)" if args.tp_shapes else ""),
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
                        "cuda_graph": graph is not None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -394,6 +398,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp-shapes", type=int, default=0, help="debug: run rank 0's shard shapes of a TP-N token on one GPU without the all-reduce")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     cfg = MODELS[args.model]
