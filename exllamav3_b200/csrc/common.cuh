@@ -51,11 +51,11 @@ struct DevCtx
     uint8_t* tmap_slots = nullptr;   // NUM_SLOTS x TMAP_SLOTS x 128 B: per-CTA patched tensor maps of multi-matrix launches
     static constexpr int TMAP_SLOTS = 256;
     uint8_t* tmap_slot(int s) { return tmap_slots + (size_t) s * TMAP_SLOTS * 128; }
-    // i8 path split-K exchange: NUM_SLOTS x I8_PART_CTAS slots of 4 x 128 fp32, all-ones (sentinel) whenever no launch is
+    // i8 path split-K exchange: NUM_SLOTS x I8_PART_CTAS slots of up to 8 x 128 fp32, all-ones (sentinel) whenever no launch is
     // in flight: contributors overwrite, the strip's reducer reads and restores the sentinel
     float* i8_parts = nullptr;
     static constexpr int I8_PART_CTAS = 256;
-    float* i8_parts_slot(int s) { return i8_parts + (size_t) s * I8_PART_CTAS * 512; }
+    float* i8_parts_slot(int s) { return i8_parts + (size_t) s * I8_PART_CTAS * 1024; }
     uint64_t launch_seq = 0;
     int next_slot() { return (int) (launch_seq++ % NUM_SLOTS); }
     float* ws_slot(int s) { return (float*) ((char*) ws + (size_t) s * WS_BYTES_PER_SLOT); }

@@ -1,4 +1,4 @@
-// tcgen05 kind::i8 EXL3 decode-GEMM for the mul1 codebook, m <= 4 ("TC-i8 path", tag 210).
+// tcgen05 kind::i8 EXL3 decode-GEMM for the mul1 codebook, m <= 4 (instantiated for up to 8 rows, see api.cu) ("TC-i8 path", tag 210).
 //
 // Why: the bit-exact mul1 decode needs IMAD + IDP.4A per weight on the same issue pipe plus pack + HFMA2; measured
 // (profiles/r01_microbench_pipes.log) that caps the decode at ~20 weights/clk/SM = ~45 % of the HBM rate at K = 4.
@@ -27,14 +27,16 @@ namespace exl3b {
 
 using namespace ptx;
 
-constexpr int I8_MAX_M = 4;
+constexpr int I8_MAX_M = 8;                                    // rows per launch: kernel instantiated for MR = 4 and MR = 8 rows
 constexpr int I8_A_STAGE_COLS = 128;
 constexpr int I8_A_STAGES = 3;
 constexpr int I8_DEC_GROUPS = 2;
 constexpr int I8_D_COL0 = I8_A_STAGES * I8_A_STAGE_COLS;      // 384
 constexpr int I8_NT = 16;                                      // N: rows 2r = hi digit, 2r+1 = lo digit of row r
-constexpr int I8_B_BYTES = 4096;                               // one row group: 32 K-chunks x (8 rows x 16 B)
-constexpr int I8_B_STAGE = I8_B_BYTES + 64;                    // + per-row digit sums of the unit
+// digit tile of a unit: 32 K-chunks x (8 N-rows x 16 B) per row group; N-rows 2r / 2r+1 = hi / lo digit of activation row r, so
+// MR = 4 rows fill one row group (4096 B) and MR = 8 rows two (SBO = 4096 B); + 64 B of per-row digit sums behind the tile
+__host__ __device__ constexpr int i8_b_bytes(int MR) { return MR <= 4 ? 4096 : 8192; }
+__host__ __device__ constexpr int i8_b_stage(int MR) { return i8_b_bytes(MR) + 64; }
 constexpr int I8_SUB_UNITS = 96;                               // int32 accumulator safety: <= 12288 k per accumulation
 constexpr uint32_t I8_SENTINEL = 0xffffffffu;                  // "no partial sum here yet" in the split-K exchange buffer
 constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 256 + 0  -> hi in [-127, 127]
@@ -44,19 +46,20 @@ constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 2
 // (measured: the two transform warps were the per-unit critical path, ~900 cycles of latency per unit each)
 constexpr int I8_CACHE_MAX_BYTES = 64 * 1024;
 
-__host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int stages, int cache_bytes)
+__host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int MR, int stages, int cache_bytes)
 {
-    TcSmemLayout L = tc_smem_layout(K, I8_B_STAGE, stages);
+    TcSmemLayout L = tc_smem_layout(K, i8_b_stage(MR), stages);
     L.total += cache_bytes;            // cache lives after the barrier block, at the old L.total
     return L;
 }
 
-template <int K>
+template <int K, int MR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const TcSmemLayout L = i8_smem_layout(K, p.stages, 0);          // offsets only; the cache starts at L.total
+    constexpr int I8_B_BYTES = i8_b_bytes(MR);
+    const TcSmemLayout L = i8_smem_layout(K, MR, p.stages, 0);          // offsets only; the cache starts at L.total
     const bool cached = p.b_load_bytes > 0;                            // host: cache_bytes (0 = recompute per unit)
     half* xh_cache = reinterpret_cast<half*>(smem + L.total);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,14 +71,14 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const half* suh = p.suh; const half* svh = p.svh; const half* A_raw = p.A_raw;
     char* Cout = (char*) p.C; float* ws = p.ws; int* counters = p.counters;
     const bool multi = p.num_mats > 0;
-    float* const parts = p.parts;                    // split-K exchange buffer, one slot of I8_MAX_M x 128 floats per CTA of the grid
+    float* const parts = p.parts;                    // split-K exchange buffer, one slot of MR x 128 floats per CTA of the grid
     int cta0 = 0;                                    // first CTA of this matrix's group
     if (multi)
     {
         G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G;
         suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
         A_raw += (size_t) mat * p.a_mat_stride; Cout += (size_t) mat * p.c_mat_stride;
-        ws += (size_t) mat * 2 * G * (I8_MAX_M * 128); counters += mat * (p.n / 128);
+        ws += (size_t) mat * 2 * G * (MR * 128); counters += mat * (p.n / 128);
     }
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -89,8 +92,8 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-    unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [I8_MAX_M] float bits, >= 0
-    int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                            // [2][I8_MAX_M] digit sums per D buffer
+    unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [MR] float bits, >= 0
+    int* s_tout = reinterpret_cast<int*>(tmem_slot + 12);                           // [2][MR] digit sums per D buffer
 
 #ifdef EXL3B_TC_DEBUG
     const int KNOB = p.knob_;
@@ -121,7 +124,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         for (int s = lane; s < S; s += 32) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / I8_DEC_GROUPS + 1); }
         if (lane < 4) { mbar_init(A_FULL(lane), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(lane), 1); }
         else if (lane < 6) { mbar_init(D_FULL(lane - 4), 1); mbar_init(D_EMPTY(lane - 4), 4); }
-        else if (lane < 6 + I8_MAX_M) s_absmax[lane - 6] = 0u;
+        else if (lane < 6 + MR) s_absmax[lane - 6] = 0u;
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -138,13 +141,11 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     const int n_units = (int) (uend - ubeg);
 
     // fp16 transformed activation of (row r, k-block kb), 4 values per lane, exactly as the reference's A_had
-    auto xh_block = [&](int r, int kb, float (&v)[4])
+    auto xh_finish = [&](uint2 raw, uint2 scb, float (&v)[4])
     {
-        uint2 raw = *reinterpret_cast<const uint2*>(A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
         half2 a = *reinterpret_cast<half2*>(&raw.x), b = *reinterpret_cast<half2*>(&raw.y);
         if (suh)
         {
-            const uint2 scb = *reinterpret_cast<const uint2*>(suh + kb * 128 + lane * 4);
             a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
             b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
             float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
@@ -153,6 +154,27 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             b = __floats2half2_rn(v2 * R_SCALE, v3 * R_SCALE);
         }
         v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    };
+    auto xh_block = [&](int r, int kb, float (&v)[4])
+    {
+        const uint2 raw = *reinterpret_cast<const uint2*>(A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
+        uint2 scb = make_uint2(0, 0);
+        if (suh) scb = *reinterpret_cast<const uint2*>(suh + kb * 128 + lane * 4);
+        xh_finish(raw, scb, v);
+    };
+    // one transformed block: into the cache, its |max| into the row maximum
+    auto xh_publish = [&](int r, int kb, const float (&v)[4])
+    {
+        if (cached)
+        {
+            const half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);     // exact: values are fp16
+            uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4) = o;
+        }
+        float mx = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) atomicMax(&s_absmax[r], __float_as_uint(mx));
     };
 
     // ---- prologue: per-row max |xh| over the whole row (warps 2..19), overlapped with the first weight loads ----
@@ -164,21 +186,41 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     {
         pdl_wait();                                       // A is produced by the previous kernel
         const int nw = TC_EPI_WARP0 - TC_XF_WARP0;       // 18 warps
-        for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
+        if constexpr (MR <= 4)
         {
-            const int r = task / KB, kb = task % KB;
-            float v[4];
-            xh_block(r, kb, v);
-            if (cached)
+            for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
             {
-                const half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);     // exact: values are fp16
-                uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
-                *reinterpret_cast<uint2*>(xh_cache + (size_t) r * p.k + kb * 128 + lane * 4) = o;
+                const int r = task / KB, kb = task % KB;
+                float v[4];
+                xh_block(r, kb, v);
+                xh_publish(r, kb, v);
             }
-            float mx = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) atomicMax(&s_absmax[r], __float_as_uint(mx));
+        }
+        else
+        {
+            // up to 8 rows: one k-block of ALL rows per step, the rows' loads in flight together (one L2 round trip per step
+            // instead of one per row)
+            for (int kb = warp - TC_XF_WARP0; kb < KB; kb += nw)
+            {
+                uint2 scb = make_uint2(0, 0), raw[MR];
+                if (suh) scb = *reinterpret_cast<const uint2*>(suh + kb * 128 + lane * 4);
+                #pragma unroll
+                for (int r = 0; r < MR; ++r)
+                {
+                    raw[r] = make_uint2(0, 0);
+                    if (r < p.m) raw[r] = *reinterpret_cast<const uint2*>(A_raw + (size_t) r * p.k + kb * 128 + lane * 4);
+                }
+                #pragma unroll
+                for (int r = 0; r < MR; ++r)
+                {
+                    if (r < p.m)
+                    {
+                        float v[4];
+                        xh_finish(raw[r], scb, v);
+                        xh_publish(r, kb, v);
+                    }
+                }
+            }
         }
         asm volatile("bar.sync 2, %0;" :: "n"((TC_EPI_WARP0 - TC_XF_WARP0) * 32) : "memory");
         if (warp == TC_DEC_WARP0 && lane == 0) stamp(2);
@@ -271,7 +313,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (sub_left == 0)
             {
                 tsum += tload; tload = 0;
-                if (lane < p.m) s_tout[dbuf * I8_MAX_M + lane] = tsum;      // visible to the epilogue before D_FULL fires
+                if (lane < p.m) s_tout[dbuf * MR + lane] = tsum;      // visible to the epilogue before D_FULL fires
                 __threadfence_block();
                 __syncwarp();
             }
@@ -311,9 +353,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     {
         // =========================== activation digits (per unit) ===========================
         const int xw = warp - TC_XF_WARP0;
-        float inv_scale[I8_MAX_M];
+        float inv_scale[MR];
         #pragma unroll
-        for (int r = 0; r < I8_MAX_M; ++r)
+        for (int r = 0; r < MR; ++r)
         {
             const float mx = __uint_as_float(s_absmax[r]);
             inv_scale[r] = mx > 0.f ? (float) I8_QMAX / mx : 0.f;
@@ -326,9 +368,11 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             I8_WAITCNT(wf_a, W_EMPTY(s), ph ^ 1);
             mbar_wait<64>(W_EMPTY(s), ph ^ 1);
             uint8_t* dst = smem + L.off_b + s * L.b_bytes;
+            int qsum[MR];
             #pragma unroll
-            for (int r = 0; r < I8_MAX_M; ++r)
+            for (int r = 0; r < MR; ++r)
             {
+                qsum[r] = 0;
                 if (r < p.m && !(KNOB & 8))
                 {
                     float v[4];
@@ -351,13 +395,26 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                         hi_w[e] = (uint32_t) (hi & 0xff) * 0x01010101u;          // digit replicated over the 4 product bytes
                         lo_w[e] = (uint32_t) (lo & 0xff) * 0x01010101u;
                     }
-                    // chunk = lane (4 k-values x 4 bytes = 16 B), rows 2r (hi) and 2r+1 (lo) of row group 0
-                    *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r) * 16) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-                    *reinterpret_cast<uint4*>(dst + (lane * 8 + 2 * r + 1) * 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-                    #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
-                    if (lane == 0) *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * r) = qs;
+                    // chunk = lane (4 k-values x 4 bytes = 16 B), N-rows 2r (hi) and 2r+1 (lo): row group r / 4, local rows 2 (r % 4), +1
+                    uint8_t* drow = dst + (r >> 2) * 4096 + (lane * 8 + 2 * (r & 3)) * 16;
+                    *reinterpret_cast<uint4*>(drow) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+                    *reinterpret_cast<uint4*>(drow + 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+                    qsum[r] = qs;
                 }
+            }
+            // digit sums of all rows: the butterfly steps of different rows are independent, issued side by side
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                #pragma unroll
+                for (int r = 0; r < MR; ++r) qsum[r] += __shfl_xor_sync(0xffffffffu, qsum[r], o);
+            }
+            if (lane < p.m)
+            {
+                int mine = 0;
+                #pragma unroll
+                for (int r = 0; r < MR; ++r) if (lane == r) mine = qsum[r];
+                *reinterpret_cast<int*>(dst + I8_B_BYTES + 4 * lane) = mine;
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -444,7 +501,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
         float* tile = reinterpret_cast<float*>(smem + L.off_tile);
         auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
-        const int part_stride = I8_MAX_M * 128;
+        const int part_stride = MR * 128;
 
         // the prologue result is needed here too: wait for it through the first D_FULL (the MMA warp only gets
         // operands after the transform warps passed the prologue barrier), then read the maxima
@@ -455,8 +512,8 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         auto emit_rows = [&](int strip)
         {
             epi_bar();
-            if (q < p.m)
-                output_row_128(tile + q * 128, Cout, (size_t) q * p.n + strip * 128,
+            for (int r = q; r < p.m; r += 4)
+                output_row_128(tile + r * 128, Cout, (size_t) r * p.n + strip * 128,
                                svh ? svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
             epi_bar();
         };
@@ -474,9 +531,9 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             const int n_contrib = c_b - c_a + 1;
             const bool full = n_contrib == 1;
 
-            float facc[I8_MAX_M];
+            float facc[MR];
             #pragma unroll
-            for (int r = 0; r < I8_MAX_M; ++r) facc[r] = 0.f;
+            for (int r = 0; r < MR; ++r) facc[r] = 0.f;
             for (int done = 0; done < seg; )
             {
                 const int sub = (seg - done) < I8_SUB_UNITS ? (seg - done) : I8_SUB_UNITS;
@@ -487,11 +544,11 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 tmem_ld_32x32b_x16(tmem_base + lane_base + I8_D_COL0 + dbuf * I8_NT, rr);
                 tc_wait_ld();
                 #pragma unroll
-                for (int r = 0; r < I8_MAX_M; ++r)
+                for (int r = 0; r < MR; ++r)
                 {
                     if (r < p.m)
                     {
-                        const int T = s_tout[dbuf * I8_MAX_M + r];
+                        const int T = s_tout[dbuf * MR + r];
                         // sum_k q_k (bytesum_kn - 510), exact in 64-bit
                         const long long sp = 256ll * (int) rr[2 * r] + (long long) (int) rr[2 * r + 1] - 510ll * T;
                         const float mx = __uint_as_float(s_absmax[r]);
@@ -509,7 +566,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
             if (full)
             {
                 #pragma unroll
-                for (int r = 0; r < I8_MAX_M; ++r) if (r < p.m) tile[r * 128 + col] = facc[r];
+                for (int r = 0; r < MR; ++r) if (r < p.m) tile[r * 128 + col] = facc[r];
                 emit_rows(strip);
             }
             else if (cta != c_a)
@@ -517,7 +574,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 // Contributor: publish the partial sums and move on.  The data is its own flag: the exchange buffer holds the
                 // sentinel everywhere outside a launch, a 32-bit store is single-copy atomic, so no fence, counter or ticket.
                 #pragma unroll
-                for (int r = 0; r < I8_MAX_M; ++r)
+                for (int r = 0; r < MR; ++r)
                     if (r < p.m)
                     {
                         uint32_t bits = __float_as_uint(facc[r]);
@@ -532,7 +589,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
                 // natural reducer: own sums from registers, then the others' in fixed CTA order (bit-reproducible).  One global
                 // round trip in the common case -- the old protocol needed three (fence + ticket, then the loads).
                 #pragma unroll
-                for (int r = 0; r < I8_MAX_M; ++r)
+                for (int r = 0; r < MR; ++r)
                 {
                     if (r < p.m)
                     {
@@ -602,14 +659,14 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 
-template <int K>
-static cudaError_t i8_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap)
+template <int K, int MR>
+static cudaError_t i8_launch_mr(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap)
 {
     static bool attr_set[32] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (!attr_set[dev & 31])
     {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_i8_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_i8_kernel<K, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 31] = true;
     }
@@ -619,12 +676,21 @@ static cudaError_t i8_launch(cudaStream_t stream, int grid, int smem_bytes, cons
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_i8_kernel<K>, p, tmap);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_i8_kernel<K, MR>, p, tmap);
 }
+
+template <int K>
+static cudaError_t i8_launch(cudaStream_t stream, int grid, int smem_bytes, const TcParams& p, const CUtensorMap& tmap)
+{
+    return p.m <= 4 ? i8_launch_mr<K, 4>(stream, grid, smem_bytes, p, tmap) : i8_launch_mr<K, 8>(stream, grid, smem_bytes, p, tmap);
+}
+
+// rows 5..8 need the whole transformed activation cached in shared memory (the per-unit digit warps cannot afford eight Hadamards)
+static bool i8_rows_ok(int m, int k) { return m >= 1 && (m <= 4 || (m <= I8_MAX_M && (size_t) m * k * 2 <= I8_CACHE_MAX_BYTES)); }
 
 bool gemm_tc_i8_supported(const GemmArgs& a)
 {
-    return a.cb == 2 && a.m >= 1 && a.m <= I8_MAX_M && a.k >= 128 && a.n >= 128 && a.k % 128 == 0 && a.n % 128 == 0;
+    return a.cb == 2 && i8_rows_ok(a.m, a.k) && a.k >= 128 && a.n >= 128 && a.k % 128 == 0 && a.n % 128 == 0;
 }
 
 int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
@@ -637,15 +703,16 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
     p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
     p.parts = ctx->i8_parts_slot(slot);
-    const int stage_bytes = 2048 * a.K + I8_B_STAGE;
+    const int MR = a.m <= 4 ? 4 : 8;
+    const int stage_bytes = 2048 * a.K + i8_b_stage(MR);
     int cache_bytes = a.m * a.k * 2;
     cache_bytes = (cache_bytes + 127) / 128 * 128;
     if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
     int stages = (200 * 1024 - cache_bytes) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) stages = 2;
-    p.stages = stages; p.b_bytes = I8_B_STAGE; p.b_load_bytes = cache_bytes;
-    const TcSmemLayout L = i8_smem_layout(a.K, stages, cache_bytes);
+    p.stages = stages; p.b_bytes = i8_b_stage(MR); p.b_load_bytes = cache_bytes;
+    const TcSmemLayout L = i8_smem_layout(a.K, MR, stages, cache_bytes);
     EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): shared-memory budget exceeded");
     const long long U = (long long) (a.k / 128) * (a.n / 128);
     int grid = ctx->num_sms;
@@ -673,7 +740,7 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 bool mgemm_tc_i8_supported(const DevCtx* ctx, const MGemmArgs& a)
 {
     // dense case only: one output per matrix, shared or per-matrix input, no routing / weighting / ragged widths
-    if (a.cb != 2 || a.m < 1 || a.m > I8_MAX_M) return false;
+    if (a.cb != 2 || !i8_rows_ok(a.m, a.k)) return false;
     if (a.indices || a.weights || a.size_n_list || a.min_index >= 0 || a.num_tokens != 1) return false;
     if (a.bszm_out < 1 || !(a.bszm_in == 1 || a.bszm_in == a.bszm_out)) return false;
     if (a.bszm_out > ctx->num_sms || a.bszm_out > DevCtx::TMAP_SLOTS) return false;
@@ -701,15 +768,16 @@ int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
     p.c_mat_stride = (long long) a.m * a.n * (a.c_fp32 ? 4 : 2);
     p.tmap_slots = ctx->tmap_slot(slot);
     p.parts = ctx->i8_parts_slot(slot);
-    const int stage_bytes = 2048 * a.K + I8_B_STAGE;
+    const int MR = a.m <= 4 ? 4 : 8;
+    const int stage_bytes = 2048 * a.K + i8_b_stage(MR);
     int cache_bytes = a.m * a.k * 2;
     cache_bytes = (cache_bytes + 127) / 128 * 128;
     if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
     int stages = (200 * 1024 - cache_bytes) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) stages = 2;
-    p.stages = stages; p.b_bytes = I8_B_STAGE; p.b_load_bytes = cache_bytes;
-    const TcSmemLayout L = i8_smem_layout(a.K, stages, cache_bytes);
+    p.stages = stages; p.b_bytes = i8_b_stage(MR); p.b_load_bytes = cache_bytes;
+    const TcSmemLayout L = i8_smem_layout(a.K, MR, stages, cache_bytes);
     EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_mgemm (i8): shared-memory budget exceeded");
     const long long U = (long long) (a.k / 128) * (a.n / 128);
     int gpm = ctx->num_sms / mats;

@@ -45,7 +45,7 @@ enum exl3b_status
 #define EXL3B_TAG_NOP 0        /* empty problem                                            */
 #define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
 #define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
-#define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path (mul1, m <= 4)            */
+#define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path: mul1, m <= 4 (auto); m <= 8 with m*k <= 32768 when forced */
 
 int exl3b_abi_version(void);
 

@@ -277,10 +277,11 @@ def test_mgemm_modes(cuda):
 
 
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
-@pytest.mark.parametrize("m", [1, 2, 4])
+@pytest.mark.parametrize("m", [1, 2, 4, 5, 8])
 def test_gemm_i8_tensor_core_path(cuda, K, m):
     """
-    mul1 int8 tensor-core codebook path (tag 210, default for mul1 at m <= 4).  Two bars:
+    mul1 int8 tensor-core codebook path (tag 210, default for mul1 at m <= 4, and at m <= 8 while the transformed rows fit
+    the kernel's shared-memory cache).  Two bars:
       * implementation: agrees with the exact integer model of the path (oracle.exl3_gemm_i8_model) to fp32 round-off
       * approximation: distance to the fp64 oracle of the reference math  max-abs <= 2e-3 max|y|, rel-RMS <= 1e-3
         (the skipped per-weight fp16 rounding; the reference's own default int8 GEMV deviates ~9e-3, exl3_gemv_int8.cu:19-20)
@@ -308,10 +309,10 @@ def test_gemm_i8_tensor_core_path(cuda, K, m):
         assert float(np.abs(y[1]).max()) == 0.0
         for r in (0, 2):
             assert rel_err(y[r:r + 1], ref[r:r + 1])[0] <= 2e-3
-        # forcing the path outside its domain (m > 4) is an error, not a silent fallback
+        # forcing the path outside its domain (m > 8) is an error, not a silent fallback
         with pytest.raises(RuntimeError, match="int8 tensor-core path forced"):
-            ext.exl3_gemm(T(np.zeros((5, 512), np.float16), cuda), T(tr, cuda),
-                          torch.empty((5, 256), dtype=torch.half, device=cuda), T(suh, cuda), None, T(svh, cuda),
+            ext.exl3_gemm(T(np.zeros((9, 512), np.float16), cuda), T(tr, cuda),
+                          torch.empty((9, 256), dtype=torch.half, device=cuda), T(suh, cuda), None, T(svh, cuda),
                           -1, False, True, 0)
     finally:
         ext.set_gemm_path(prev)

@@ -17,8 +17,9 @@ for (k, n, K, copies) in shapes:
     g = torch.Generator(device=dev); g.manual_seed(1)
     trs = [torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16) for _ in range(copies)]
     suh = torch.ones(k, dtype=torch.half, device=dev); svh = torch.ones(n, dtype=torch.half, device=dev)
-    x = torch.randn((1, k), generator=g, device=dev).half(); xh = torch.empty_like(x)
-    y = torch.empty((1, n), dtype=torch.float, device=dev)
+    M = int(os.environ.get("M", "1"))
+    x = torch.randn((M, k), generator=g, device=dev).half(); xh = torch.empty_like(x)
+    y = torch.empty((M, n), dtype=torch.float, device=dev)
     row = {}
     for kn in knobs:
         lib.exl3b_debug_tc_knob(kn)
