@@ -18,9 +18,19 @@
 // the fp16 kernel than that.  Tolerances are asserted in tests/test_gpu_parity.py::test_gemm_i8_*.
 //
 // Structure is the same as gemm_tc.cu (stream-K units of 128x128 weights, TMA ring, TMEM operand stages, warp roles);
-// differences: A stage = 128 TMEM columns (one 32-bit product per weight), 16 MMAs (K = 32 bytes = 8 weights) per
-// unit, a CTA prologue that finds the per-row |xh| maximum (all 18 non-issuer warps, redundantly per CTA: m <= 4),
-// per-unit activation digits + digit sums written by the transform warps, int32 accumulators.
+// differences:
+//   * A stage = 128 TMEM columns (one 32-bit product per weight, three stages), 16 MMAs (K = 32 bytes = 8 weights) per unit
+//     issued from one stepped shared-memory descriptor (one uniform add per MMA), int32 accumulators
+//   * a CTA prologue (warps 2..19, redundantly per CTA) transforms the rows once into a shared-memory cache and finds the
+//     per-row |xh| maximum; the two transform warps then write per-unit activation digits + digit sums
+//   * the decode group's lead warp waits for the digits before it arrives on A_FULL, so the MMA warp polls one barrier per unit
+//   * split-K partial sums travel through a sentinel-armed exchange buffer: contributors store and leave, the CTA owning the
+//     strip's first k-segment (it processes it last) adds them to its registers in fixed CTA order and re-arms the slots --
+//     no fence, no ticket, one global round trip, bit-reproducible
+//   * multi-matrix launches (dense exl3_mgemm: the model's k+v and gate+up calls): the grid is cut into one CTA group per
+//     matrix; the pointer tables stay in device memory, each CTA patches the weight tensor map's address on the device
+//   * instantiated for MR = 4 and MR = 8 activation rows (digit tile with one / two row groups); api.cu auto-selects m <= 4
+// Measured history and the experiments that were not kept: profiles/r01_ncu_notes.md.
 #include "tc_common.cuh"
 
 namespace exl3b {
@@ -69,7 +79,7 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     // launch of g_per_mat CTAs; `cta` is the index inside the group
     int cta = blockIdx.x, G = gridDim.x, mat = 0;
     const half* suh = p.suh; const half* svh = p.svh; const half* A_raw = p.A_raw;
-    char* Cout = (char*) p.C; float* ws = p.ws; int* counters = p.counters;
+    char* Cout = (char*) p.C;
     const bool multi = p.num_mats > 0;
     float* const parts = p.parts;                    // split-K exchange buffer, one slot of MR x 128 floats per CTA of the grid
     int cta0 = 0;                                    // first CTA of this matrix's group
@@ -78,7 +88,6 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
         G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G;
         suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
         A_raw += (size_t) mat * p.a_mat_stride; Cout += (size_t) mat * p.c_mat_stride;
-        ws += (size_t) mat * 2 * G * (MR * 128); counters += mat * (p.n / 128);
     }
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -91,7 +100,6 @@ gemm_tc_i8_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap_w)
     auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
     auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
-    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
     unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [MR] float bits, >= 0
     int* s_tout = reinterpret_cast<int*>(tmem_slot + 12);                           // [2][MR] digit sums per D buffer
 
