@@ -198,7 +198,11 @@ class Token:
         self.first_x = self.mats[0]["x"]
         self.logits = self.mats[-1]["y"]
         # launch list.  k+v and gate+up share their input and shape: the reference's model code issues them as ONE
-        # exl3_mgemm each at bsz*q_len <= 32 (modules/attn.py:603-631 multi_kv, modules/mlp.py:726-760 multi_gu)
+        # exl3_mgemm each at bsz*q_len <= 32 (modules/attn.py:603-631 multi_kv, modules/mlp.py:726-760 multi_gu) whenever
+        # config.use_mgemm() says so (model/config.py:48-64): always for narrow outputs (k+v), and for gate+up when
+        # ext.exl3_gemv_int8_max_k(device) < K -- the reference's own extension answers 6 on Blackwell (its separate int8 GEMVs
+        # beat its fused kernel), this library's shim answers 0 (the fused launch is the faster one here), so through the
+        # drop-in boundary the model issues exactly this launch list.  --no-fuse times one launch per projection.
         self.launches = []
         i = 0
         while i < len(self.mats):
@@ -360,7 +364,8 @@ def run_gpu_arm(args, cfg):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.model} EXL3 4.0bpw (lm_head 6bpw) b=1 decode: "
                                    f"{len(tok.mats)} quantized matrices/token in {len(tok.launches)} launches "
-                                   f"(k+v and gate+up as exl3_mgemm like the reference's decode path), m=1, mul1 codebook, "
+                                   f"(k+v and gate+up as one exl3_mgemm each: what the reference's model code issues through this library's "
+                                   f"ext shim, model/config.py:48-64), m=1, mul1 codebook, "
                                    f"random-init trellis",
                        "parallelism": (f"tp{world}" if world > 1 else "single") + (f" (DRY RUN of tp{args.tp_shapes} rank-0 shapes, no collective: not a result)" if args.tp_shapes else ""),
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),

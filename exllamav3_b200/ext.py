@@ -264,6 +264,18 @@ def g_get_num_sms(device: int) -> int:
     return _check(_lib.exl3b_num_sms(int(device)))
 
 
+def exl3_gemv_int8_max_k(device: int) -> int:
+    """
+    The reference's model code asks this to decide whether same-input projections (k+v, gate+up) go out as ONE fused
+    exl3_mgemm or as separate calls: it unfuses mul1 tensors with K <= this value because its separate int8 GEMVs beat its
+    fused kernel there (model/config.py:48-64 use_mgemm, exllamav3_ext/quant/exl3_gemv_int8.cu:46-52: 6 on Blackwell).
+    Here the fused launch is always the faster one (one launch of the same tensor-core kernel, CTA groups per matrix;
+    profiles/r01_ncu_notes.md item 10), so the answer is 0: use_mgemm() then returns True for every K.
+    """
+    _check(_lib.exl3b_num_sms(int(device)))          # same failure mode as the reference on a bad device index
+    return 0
+
+
 def exl3_gemm_num_kernel_shapes() -> int:
     """The reference enumerates 4 mma.sync tile shapes (exl3_kernel_map.cuh:53-60); here: SIMT and tcgen05 paths."""
     return 2

@@ -64,8 +64,19 @@ def test_reference_named_surface_is_complete():
     from exllamav3_b200 import ext
     for name in ["exl3_gemm", "exl3_mgemm", "reconstruct", "reconstruct_slice", "reconstruct_had_slice",
                  "had_r_128", "hgemm", "BC_LinearEXL3", "g_get_cc", "g_get_num_sms",
-                 "exl3_gemm_num_kernel_shapes", "exl3_gemm_shape_compat"]:
+                 "exl3_gemm_num_kernel_shapes", "exl3_gemm_shape_compat", "exl3_gemv_int8_max_k"]:
         assert hasattr(ext, name), name
+
+
+def test_use_mgemm_policy_through_the_shim():
+    """model/config.py:48-64 (use_mgemm): for mul1 tensors the reference fuses k+v / gate+up into one exl3_mgemm iff
+    K >= ext.exl3_gemv_int8_max_k(device) + 1 or the output is narrow.  The shim reports 0 => fused for every K."""
+    from exllamav3_b200 import ext
+    import inspect
+    src = inspect.getsource(ext.exl3_gemv_int8_max_k)
+    assert "return 0" in src
+    k_thr = 0 + 1
+    assert all(K >= k_thr for K in range(1, 9))
 
 
 def test_linear_exl3_tp_slice_host_logic():
