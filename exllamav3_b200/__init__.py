@@ -7,8 +7,13 @@ exllamav3_b200 -- Blackwell-native (sm_100a) EXL3 quantized-GEMM path.
     MultiLinear   pointer tables for exl3_mgemm (exllamav3.modules.multilinear.MultiLinear)
     tp            column/row tensor-parallel shard + NCCL all-reduce around the row-parallel output
 """
-from . import ext
-from .linear_exl3 import LinearEXL3, AUTO_RECONSTRUCT_THRESHOLD
-from .multilinear import MultiLinear
+import sys as _sys
+
+# `python -m exllamav3_b200.build` imports this package before the library exists: only then skip the operator surface
+# (everything else fails loudly in ext.py when libexl3b200.so is missing -- there is no fallback implementation)
+if "exllamav3_b200.build" not in getattr(_sys, "orig_argv", ()):
+    from . import ext
+    from .linear_exl3 import LinearEXL3, AUTO_RECONSTRUCT_THRESHOLD
+    from .multilinear import MultiLinear
 
 __all__ = ["ext", "LinearEXL3", "MultiLinear", "AUTO_RECONSTRUCT_THRESHOLD"]

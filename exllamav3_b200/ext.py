@@ -7,7 +7,7 @@ behaviour (RuntimeError for shape/dtype violations) as the pybind11 bindings the
     reconstruct, reconstruct_slice, reconstruct_had_slice      bindings.cpp:122-124
     had_r_128, hgemm                           bindings.cpp:125,147
     BC_LinearEXL3                              exllamav3_ext/libtorch/linear_bc.h:13-35, linear.cpp:34-71
-    g_get_cc, g_get_num_sms, exl3_gemm_num_kernel_shapes, exl3_gemm_shape_compat     bindings.cpp:127-131
+    exl3_gemv, g_get_cc, g_get_num_sms, exl3_gemm_num_kernel_shapes, exl3_gemm_shape_compat     bindings.cpp:127-131
 
 PyTorch is plumbing only here: device memory, the current CUDA stream and the device guard.
 There is no CPU or torch fallback: if the shared library is missing this module fails to import, and every op
@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "libexl3b200.so")
 
 if not os.path.exists(_LIB_PATH):
     raise ImportError(
-        f"{_LIB_PATH} not found: build it with `python -m exllamav3_b200.build` "
+        f"{_LIB_PATH} not found: build it with `python -m exllamav3_b200.build` (or `python __graft_entry__.py`) "
         "(the EXL3 path has no fallback implementation)")
 
 _lib = ctypes.CDLL(_LIB_PATH)
@@ -254,6 +254,26 @@ def hgemm(a, b, c) -> None:
     with torch.cuda.device(a.device):
         _check(_lib.exl3b_hgemm(_stream(a), _ptr(a), _ptr(b), _ptr(c), m, k, n, int(c.dtype == torch.float),
                                 c.stride(-2)))
+
+
+def exl3_gemv(A, B, C, suh, A_had, svh, mcg, mul1) -> None:
+    """
+    Direct entry of the reference's small-m GEMV kernel, exposed for testing (exllamav3_ext/quant/exl3_gemv.cu:171-243,
+    bindings.cpp:127): errors if the call is not hard-eligible for that kernel (suh/A_had/svh given, m <= 8, K in 2..4,
+    k % 128 == 0, n % 128 == 0; exl3_gemv.cu:36-47,198).  Here small-m calls have no separate kernel family -- the
+    tcgen05 decode-GEMM is the small-m kernel -- so the same eligibility rules are enforced and the call is exl3_gemm.
+    """
+    _need_cuda(A, B, C, suh, A_had, svh)
+    if B.dim() != 3:
+        raise RuntimeError("B: incorrect number of dimensions, must be 3")
+    if suh is None or A_had is None or svh is None:
+        raise RuntimeError("exl3_gemv requires suh, A_had and svh")
+    size_k = A.shape[-1]
+    size_m = A.numel() // size_k if size_k else 0
+    size_n, K = B.shape[1] * 16, B.shape[2] // 16
+    if not (1 <= size_m <= 8 and 2 <= K <= 4 and size_k % 128 == 0 and size_n % 128 == 0):
+        raise RuntimeError("exl3_gemv: call not eligible (needs m <= 8, K in 2..4, k % 128 == 0, n % 128 == 0)")
+    exl3_gemm(A, B, C, suh, A_had, svh, -1, mcg, mul1, 0)
 
 
 def g_get_cc(device: int) -> int:

@@ -64,7 +64,7 @@ def test_reference_named_surface_is_complete():
     from exllamav3_b200 import ext
     for name in ["exl3_gemm", "exl3_mgemm", "reconstruct", "reconstruct_slice", "reconstruct_had_slice",
                  "had_r_128", "hgemm", "BC_LinearEXL3", "g_get_cc", "g_get_num_sms",
-                 "exl3_gemm_num_kernel_shapes", "exl3_gemm_shape_compat", "exl3_gemv_int8_max_k"]:
+                 "exl3_gemm_num_kernel_shapes", "exl3_gemm_shape_compat", "exl3_gemv_int8_max_k", "exl3_gemv"]:
         assert hasattr(ext, name), name
 
 
