@@ -179,6 +179,7 @@ class Token:
         from exllamav3_b200 import ext
         self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
         self.skip_reduce = False
+        self.fused_reduce = False           # row-parallel outputs: one kernel (GEMM + NVLink exchange) instead of GEMM + NCCL
         g = torch.Generator(device=dev); g.manual_seed(seed + rank)
         layer, head = token_plan(cfg, tp)
         self.mats = []
@@ -225,6 +226,9 @@ class Token:
         for ln in self.launches:
             if ln["kind"] == "gemm":
                 mt = ln["mt"]
+                if mt["reduce"] and self.fused_reduce:
+                    ext.exl3_gemm_allreduce(mt["x"], mt["tr"], mt["y"], mt["suh"], None, mt["svh"], False, True)
+                    continue
                 ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
                 if mt["reduce"] and not self.skip_reduce:
                     import torch.distributed as dist
@@ -250,6 +254,10 @@ def run_gpu_arm(args, cfg):
     from exllamav3_b200 import ext
 
     tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse)
+    if args.fused_allreduce and world > 1:
+        from exllamav3_b200 import tp as _tp
+        _tp.enable_fused_allreduce(max_elems=4 * cfg["hidden"])
+        tok.fused_reduce = True
     if args.tp_shapes:
         # single-GPU dry run of ONE rank's shard of a TP-N token (kernel shapes only, no collective): not a bench result
         tok.skip_reduce = True
@@ -369,7 +377,9 @@ def run_gpu_arm(args, cfg):
                                    f"random-init trellis",
                        "parallelism": (f"tp{world}" if world > 1 else "single") + (f" (DRY RUN of tp{args.tp_shapes} rank-0 shapes, no collective: not a result)" if args.tp_shapes else ""),
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
-                       "cuda_graph": graph is not None},
+                       "cuda_graph": graph is not None,
+                       "row_parallel_sum": ("fused into the GEMM epilogue over NVLink peer memory" if tok.fused_reduce else
+                                            ("NCCL all-reduce per row-parallel output" if world > 1 else "none (single GPU)"))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "gemm_tc_i8_kernel (tcgen05 kind::i8 decode-GEMM)",
                          "note": "achieved = algorithmic bytes of the step / step time = average over the step's launches of the "
@@ -403,6 +413,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-allreduce", action="store_true",
+                    help="N > 1: row-parallel outputs through exl3_gemm_allreduce (one kernel) instead of exl3_gemm + NCCL; "
+                         "opt-in until verified on hardware")
     ap.add_argument("--tp-shapes", type=int, default=0, help="debug: run rank 0's shard shapes of a TP-N token on one GPU without the all-reduce")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

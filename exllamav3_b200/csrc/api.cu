@@ -208,6 +208,44 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
     return launch_gemm_simt(stream, ctx, g);
 }
 
+int exl3b_gemm_allreduce(void* stream_, const void* A, const void* B, void* C, const void* suh, void* A_had, const void* svh,
+                         int m, int k, int n, int K, int cb, int c_fp32)
+{
+    (void) A_had;                                   // the transform runs inside the kernel (m <= 4): no scratch is written
+    int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(m >= 1 && k >= 0 && n >= 0, EXL3B_ERR_SHAPE, "exl3_gemm_allreduce: bad size");
+    EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm_allreduce: k (%d) must be divisible by 128", k);
+    EXL3B_CHECK(n % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm_allreduce: n (%d) must be divisible by 128", n);
+    EXL3B_CHECK(A && B && C, EXL3B_ERR_ARG, "exl3_gemm_allreduce: null tensor");
+    DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+    GemmArgs g{};
+    g.A = (const half*) A; g.suh = (const half*) suh; g.A_had = nullptr; g.B = (const uint32_t*) B; g.C = C; g.svh = (const half*) svh;
+    g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f; g.max_ctas = 0;
+    return launch_gemm_tc_i8_ar((cudaStream_t) stream_, ctx, g);
+}
+
+int exl3b_gemm_allreduce_check(int m, int k, int n, int K, int cb, int world, int64_t max_elems)
+{
+    const char* why = gemm_tc_i8_ar_unsupported(m, k, n, K, cb, world, (long long) max_elems);
+    EXL3B_CHECK(!why, EXL3B_ERR_UNSUPPORTED, "exl3_gemm_allreduce: %s", why ? why : "");
+    return 0;
+}
+
+int exl3b_tp_alloc(int rank, int world, int64_t max_elems, void* handle_out) { return tp_alloc(rank, world, (long long) max_elems, handle_out); }
+int exl3b_tp_attach(const void* handles, int world) { return tp_attach(handles, world); }
+int exl3b_tp_attach_loopback(void) { return tp_attach_loopback(); }
+int exl3b_tp_info(int* rank, int* world, int64_t* max_elems, int* attached)
+{
+    long long me = 0;
+    int r = tp_info(rank, world, &me, attached);
+    if (max_elems) *max_elems = me;
+    return r;
+}
+int exl3b_tp_free(void) { return tp_free(); }
+int exl3b_tp_debug_inject(void* stream, int src_rank, const void* partial, int64_t count) { return tp_debug_inject((cudaStream_t) stream, src_rank, partial, (long long) count); }
+int exl3b_tp_debug_peek(int buffer_rank, int slot, int src_rank, void* host_out, int64_t count) { return tp_debug_peek(buffer_rank, slot, src_rank, host_out, (long long) count); }
+int64_t exl3b_tp_debug_epoch(void) { return tp_debug_epoch(); }
+
 int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, const uint64_t* suh_ptrs, void* A_had,
                 const uint64_t* svh_ptrs, const int64_t* indices, int num_indices, const void* weights,
                 int bszm_in, int bszm_out, int m, int k, int n, int K, int cb, int c_fp32,

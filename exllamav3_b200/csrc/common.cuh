@@ -96,6 +96,18 @@ bool mgemm_tc_i8_supported(const DevCtx* ctx, const MGemmArgs& a);
 int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
 bool gemm_tc_i8_supported(const GemmArgs& a);
 
+// tensor-parallel row-parallel GEMM with the sum over ranks fused into the epilogue (gemm_tc_i8_ar.cu)
+int launch_gemm_tc_i8_ar(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+const char* gemm_tc_i8_ar_unsupported(int m, int k, int n, int K, int cb, int world, long long slot_elems);
+int tp_alloc(int rank, int world, long long max_elems, void* handle_out);
+int tp_attach(const void* handles, int world);
+int tp_attach_loopback();
+int tp_info(int* rank, int* world, long long* max_elems, int* attached);
+int tp_free();
+int tp_debug_inject(cudaStream_t stream, int src_rank, const void* partial, long long count);
+int tp_debug_peek(int buffer_rank, int slot, int src_rank, void* host_out, long long count);
+long long tp_debug_epoch();
+
 struct MGemmArgs
 {
     const half* A; const uint64_t* B_ptrs; void* C; const uint64_t* suh_ptrs; half* A_had; const uint64_t* svh_ptrs;

@@ -43,6 +43,24 @@ __device__ __forceinline__ void output_row_128(const float* row, char* C, size_t
         *reinterpret_cast<uint2*>((half*) C + elem_off + lane * 4) = o;
     }
 }
+
+// The same transform without the store: the fp32 values of one 128-column segment after Hadamard, scale and float(svh)
+// (the fp32-C arithmetic of output_row_128).  Used where the segment is summed over the tensor-parallel ranks first.
+__device__ __forceinline__ void finish_row_128_f32(const float* row, const half* svh, float out_scale, int lane, float (&o)[4])
+{
+    float4 v = *reinterpret_cast<const float4*>(row + lane * 4);
+    float v0 = v.x, v1 = v.y, v2 = v.z, v3 = v.w;
+    if (svh)
+    {
+        const uint2 scb = *reinterpret_cast<const uint2*>(svh + lane * 4);
+        had128_warp(v0, v1, v2, v3, lane);
+        const float r = R_SCALE * out_scale;
+        v0 *= r; v1 *= r; v2 *= r; v3 *= r;
+        const half2 a = *reinterpret_cast<const half2*>(&scb.x), b = *reinterpret_cast<const half2*>(&scb.y);
+        v0 *= __low2float(a); v1 *= __high2float(a); v2 *= __low2float(b); v3 *= __high2float(b);
+    }
+    o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+}
 #endif
 
 }  // namespace exl3b

@@ -147,6 +147,19 @@ __device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v)
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// ---- relaxed system-scope vector accesses (flag-in-data exchange between GPUs over NVLink peer memory) -------------------
+// A vector access is a set of 32-bit accesses, each of them single-copy atomic: every word is its own flag.
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint32_t* p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(uint32_t* p, uint4 v)
+{
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -48,6 +48,19 @@ struct TcParams
     unsigned long long* dbg;     // optional per-CTA timeline (16 x u64 per CTA), bring-up only
 };
 
+// Tensor-parallel group of this device for the row-parallel GEMM whose epilogue sums the ranks' partial outputs over
+// NVLink peer memory (gemm_tc_i8_ar.cu).  recv[j] = rank j's receive buffer as mapped into THIS process (recv[rank] is
+// local memory); every buffer is [AR_SLOTS][world][slot_elems] 32-bit words holding the sentinel outside a launch.
+constexpr int AR_MAX_WORLD = 8;
+constexpr int AR_SLOTS = 2;
+struct ArArgs
+{
+    uint32_t* recv[AR_MAX_WORLD];
+    unsigned int* state;         // local device memory: [0] epoch (AR launches completed), [1] CTA arrival ticket
+    long long slot_elems;        // words per (slot, source rank)
+    int rank, world;
+};
+
 struct TcSmemLayout
 {
     int w_bytes, b_bytes, off_b, off_tile, off_bars, total;

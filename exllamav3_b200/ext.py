@@ -50,11 +50,26 @@ _lib.exl3b_hgemm.restype = _i
 _lib.exl3b_gemm_host.argtypes = [_vp] * 9 + [_i] * 6
 _lib.exl3b_gemm_host.restype = _i
 
+_lib.exl3b_gemm_allreduce.argtypes = [_vp] * 7 + [_i] * 6
+_lib.exl3b_gemm_allreduce.restype = _i
+_lib.exl3b_gemm_allreduce_check.argtypes = [_i] * 6 + [_i64]
+_lib.exl3b_gemm_allreduce_check.restype = _i
+_lib.exl3b_tp_alloc.argtypes = [_i, _i, _i64, _vp]; _lib.exl3b_tp_alloc.restype = _i
+_lib.exl3b_tp_attach.argtypes = [_vp, _i]; _lib.exl3b_tp_attach.restype = _i
+_lib.exl3b_tp_attach_loopback.restype = _i
+_lib.exl3b_tp_info.argtypes = [_vp] * 4; _lib.exl3b_tp_info.restype = _i
+_lib.exl3b_tp_free.restype = _i
+_lib.exl3b_tp_debug_inject.argtypes = [_vp, _i, _vp, _i64]; _lib.exl3b_tp_debug_inject.restype = _i
+_lib.exl3b_tp_debug_peek.argtypes = [_i, _i, _i, _vp, _i64]; _lib.exl3b_tp_debug_peek.restype = _i
+_lib.exl3b_tp_debug_epoch.restype = _i64
+
 assert _lib.exl3b_abi_version() == 1
 
 EXL3B_TAG_SIMT = 100
 EXL3B_TAG_TC = 200
 EXL3B_TAG_TC_I8 = 210
+EXL3B_TAG_TC_I8_AR = 211
+TP_HANDLE_BYTES = 64
 
 lib = _lib      # raw handle for bench.py / tests (symbol export checks)
 lib_path = _LIB_PATH
@@ -128,6 +143,72 @@ def exl3_gemm(A, B, C, suh, A_had, svh, force_shape_idx: int, mcg, mul1, force_n
         return _check(_lib.exl3b_gemm(
             _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had) if suh is not None else None, _ptr(svh),
             size_m, size_k, size_n, K, _cb(mcg, mul1), int(c_fp32), int(force_shape_idx), int(force_num_sms)))
+
+
+# ---- tensor-parallel row-parallel output: GEMM + sum over ranks in one kernel (include/exl3b200.h) --------------------
+
+def tp_alloc(rank: int, world: int, max_elems: int) -> bytes:
+    """Allocate this rank's receive buffer on the current CUDA device; returns its 64-byte CUDA IPC handle."""
+    buf = ctypes.create_string_buffer(TP_HANDLE_BYTES)
+    _check(_lib.exl3b_tp_alloc(int(rank), int(world), int(max_elems), ctypes.cast(buf, _vp)))
+    return buf.raw
+
+
+def tp_attach(handles: bytes, world: int) -> None:
+    """Map the peers' receive buffers; `handles` = the world handles concatenated in rank order."""
+    if len(handles) != world * TP_HANDLE_BYTES:
+        raise RuntimeError(f"tp_attach: expected {world * TP_HANDLE_BYTES} handle bytes, got {len(handles)}")
+    buf = ctypes.create_string_buffer(bytes(handles), len(handles))
+    _check(_lib.exl3b_tp_attach(ctypes.cast(buf, _vp), int(world)))
+
+
+def tp_attach_loopback() -> None:
+    _check(_lib.exl3b_tp_attach_loopback())
+
+
+def tp_info():
+    """(rank, world, max_elems, attached) of the current device's group; rank = -1 if none."""
+    r, w, a, me = ctypes.c_int(-1), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int64(0)
+    _check(_lib.exl3b_tp_info(ctypes.addressof(r), ctypes.addressof(w), ctypes.addressof(me), ctypes.addressof(a)))
+    return r.value, w.value, me.value, bool(a.value)
+
+
+def tp_free() -> None:
+    _check(_lib.exl3b_tp_free())
+
+
+def exl3_gemm_allreduce_supported(m: int, k: int, n: int, K: int, mcg, mul1, world: int, max_elems: int) -> bool:
+    return _lib.exl3b_gemm_allreduce_check(int(m), int(k), int(n), int(K), _cb(mcg, mul1), int(world), int(max_elems)) == 0
+
+
+def exl3_gemm_allreduce(A, B, C, suh, A_had, svh, mcg, mul1) -> int:
+    """
+    Row-parallel exl3_gemm whose epilogue sums the output over the tensor-parallel ranks through NVLink peer memory:
+    one kernel instead of exl3_gemm + all_reduce (modules/mlp.py:769-770, modules/attn.py:546-547,
+    model/model_tp_backend.py:119-126).  Same tensor arguments as exl3_gemm.  Raises RuntimeError when the call is not
+    eligible (mul1, rows <= 4, group attached, rows * n within the exchange slot); the caller then uses exl3_gemm + NCCL.
+    """
+    _need_cuda(A, B, C, suh, A_had, svh)
+    if B.dim() != 3:
+        raise RuntimeError("B: incorrect number of dimensions, must be 3")
+    _dtype(A, torch.half, "A")
+    _dtype(B, torch.int16, "B")
+    c_fp32 = C.dtype == torch.float
+    if not c_fp32:
+        _dtype(C, torch.half, "C")
+    size_k = A.shape[-1]
+    size_m = A.numel() // size_k if size_k else 0
+    size_n = B.shape[1] * 16
+    if size_k != B.shape[0] * 16:
+        raise RuntimeError("A and B incompatible shapes")
+    if C.shape[-1] != size_n:
+        raise RuntimeError("C and B incompatible shapes")
+    K = B.shape[2] // 16
+    assert A.is_contiguous() and B.is_contiguous() and C.is_contiguous()
+    with torch.cuda.device(A.device):
+        return _check(_lib.exl3b_gemm_allreduce(
+            _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), None, _ptr(svh),
+            size_m, size_k, size_n, K, _cb(mcg, mul1), int(c_fp32)))
 
 
 def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_idx: int, mcg, mul1,

@@ -10,6 +10,12 @@ touches the qgemm path:
 One process per GPU, torch.distributed for the plumbing (backend "nccl" over NVLink on B200 boxes; "gloo" in the CPU
 tests).  The reference's NCCL backend casts fp32 payloads to bf16 on the wire (model/model_tp_backend.py:119-126);
 we reduce in the tensor's own dtype.
+
+Two ways to produce a row-parallel output:
+  * default: the shard's exl3_gemm, then ONE NCCL all-reduce (what the reference does);
+  * `enable_fused_allreduce()`: ONE kernel -- the decode-GEMM's epilogue exchanges every finished 128-column segment with
+    the peers over NVLink peer memory and adds the partials in rank order (csrc/gemm_tc_i8_ar.cu).  Eligible calls
+    (mul1, <= 4 rows, no bias) take it, everything else falls back to the default.  Opt-in until verified on hardware.
 """
 from __future__ import annotations
 import torch
@@ -49,8 +55,59 @@ def all_reduce(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
-def row_parallel_forward(shard, x_local: torch.Tensor, params: dict, out_dtype=None, group=None) -> torch.Tensor:
-    """y = all_reduce( shard(x[:, first:last]) ): each rank applies its own full epilogue to its partial, one sum."""
+_fused = {"on": False, "world": 1, "max_elems": 0}
+
+
+def enable_fused_allreduce(max_elems: int = 4 * 16384, group=None) -> None:
+    """
+    Set up the peer-memory exchange for the fused row-parallel GEMM on the current CUDA device: allocate the receive
+    buffer, trade the CUDA IPC handles over the (already initialised) process group, map the peers.  `max_elems` bounds
+    rows * out_features of a fused call.  Collective: every rank of the group must call it.
+    """
+    from . import ext
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handle = ext.tp_alloc(rank, world, max_elems)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    ext.tp_attach(b"".join(handles), world)
+    dist.barrier(group)                     # nobody sends before everybody has mapped
+    _fused.update(on=True, world=world, max_elems=max_elems)
+
+
+def disable_fused_allreduce(group=None) -> None:
+    from . import ext
+    if _fused["on"]:
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group)             # nobody unmaps while a peer may still write
+        ext.tp_free()
+    _fused.update(on=False, world=1, max_elems=0)
+
+
+def fused_allreduce_eligible(shard, rows: int, any_bias: bool = False) -> bool:
+    """Pure host logic (no device): would row_parallel_forward take the one-kernel path for this call?"""
+    from . import ext
+    if not _fused["on"] or any_bias or shard.bias is not None:
+        return False
+    return ext.exl3_gemm_allreduce_supported(rows, shard.in_features, shard.out_features, shard.K, shard.mcg, shard.mul1,
+                                             _fused["world"], _fused["max_elems"])
+
+
+def row_parallel_forward(shard, x_local: torch.Tensor, params: dict, out_dtype=None, group=None,
+                         any_bias: bool = False) -> torch.Tensor:
+    """
+    y = sum over ranks of shard(x[:, first:last]): each rank applies its own full epilogue to its partial, one sum.
+    `any_bias`: some rank's shard carries the bias (the reference gives it to the first shard only, exl3.py:318-321), which
+    keeps the call on the NCCL path.
+    """
+    rows = x_local.numel() // x_local.shape[-1]
+    if not params.get("reconstruct") and fused_allreduce_eligible(shard, rows, any_bias):
+        from . import ext
+        dtype = out_dtype or shard.default_out_dtype
+        y = torch.empty(tuple(x_local.shape[:-1]) + (shard.out_features,), dtype=dtype, device=x_local.device)
+        ext.exl3_gemm_allreduce(x_local.view(-1, x_local.shape[-1]), shard.trellis, y.view(-1, shard.out_features),
+                                shard.suh, None, shard.svh, shard.mcg, shard.mul1)
+        return y
     y = shard.forward(x_local, params, out_dtype)
     return all_reduce(y, group)
 

@@ -46,6 +46,7 @@ enum exl3b_status
 #define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
 #define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
 #define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path: mul1, m <= 4 (auto); m <= 8 with m*k <= 32768 when forced */
+#define EXL3B_TAG_TC_I8_AR 211 /* the same kernel with the tensor-parallel sum fused into its epilogue (exl3b_gemm_allreduce) */
 
 int exl3b_abi_version(void);
 
@@ -152,6 +153,47 @@ int exl3b_gemm_host(void* stream,
                     void* d_A, void* d_C, void* d_A_had,
                     const void* B, const void* suh, const void* svh,
                     int m, int k, int n, int K, int cb, int c_fp32);
+
+/*
+ * ---- tensor-parallel row-parallel output: GEMM + sum over ranks in ONE kernel (NVLink peer memory) ----------------------
+ *
+ * Replaces, for the row-parallel linears (o_proj, down_proj) of the reference's tensor-parallel mode, the pair
+ *     ext.exl3_gemm(...)                      exllamav3_ext/bindings.cpp:126
+ *     backend.all_reduce(y)                   exllamav3/model/model_tp_backend.py:119-126 (one NCCL launch per output),
+ * issued by exllamav3/modules/mlp.py:769-770 and exllamav3/modules/attn.py:546-547.
+ *
+ * One process per GPU.  Setup, once per process:
+ *   1. exl3b_tp_alloc(rank, world, max_elems, handle)   allocate this rank's receive buffer on the current device
+ *                                                       (max_elems >= m * n of the largest row-parallel output, multiple
+ *                                                       of 128) and get its 64-byte CUDA IPC handle
+ *   2. the ranks exchange the handles (any transport: the reference-side shim uses torch.distributed.all_gather_object)
+ *   3. exl3b_tp_attach(handles, world)                  handles = world x EXL3B_TP_HANDLE_BYTES in rank order
+ * Then exl3b_gemm_allreduce(...) = exl3b_gemm(...) followed by a sum over the ranks, every rank receiving the bit-identical
+ * result (partials are added in rank order).  Every rank must issue the same sequence of exl3b_gemm_allreduce calls.
+ * Eligibility: mul1 codebook, 1 <= m <= 4, m * n <= max_elems, world <= 8; otherwise -EXL3B_ERR_UNSUPPORTED and nothing is
+ * launched (the caller falls back to exl3b_gemm + its own all-reduce).  Returns EXL3B_TAG_TC_I8_AR.
+ * exl3b_tp_attach_loopback(): single-process bring-up -- "peer" buffers are local allocations, peer partials are supplied
+ * with exl3b_tp_debug_inject (tests only).
+ * STATUS (round 1): not yet verified on hardware; opt-in.
+ */
+#define EXL3B_TP_HANDLE_BYTES 64
+int exl3b_tp_alloc(int rank, int world, int64_t max_elems, void* handle_out);
+int exl3b_tp_attach(const void* handles, int world);
+int exl3b_tp_attach_loopback(void);
+int exl3b_tp_info(int* rank, int* world, int64_t* max_elems, int* attached);
+int exl3b_tp_free(void);
+int exl3b_gemm_allreduce(void* stream,
+                         const void* A, const void* B, void* C,
+                         const void* suh, void* A_had, const void* svh,
+                         int m, int k, int n, int K, int cb, int c_fp32);
+/* 0 if a call with these sizes can take the fused path on a group of `world` ranks with `max_elems` slots, else
+   -EXL3B_ERR_UNSUPPORTED with the reason in exl3b_last_error().  Pure host logic: needs no device. */
+int exl3b_gemm_allreduce_check(int m, int k, int n, int K, int cb, int world, int64_t max_elems);
+/* bring-up / tests: write a peer's partial (count fp32 words, device pointer) into this rank's receive buffer for the NEXT
+   exl3b_gemm_allreduce on `stream`; copy (slot, src_rank) of rank `buffer_rank`'s buffer to the host; read the epoch. */
+int exl3b_tp_debug_inject(void* stream, int src_rank, const void* partial, int64_t count);
+int exl3b_tp_debug_peek(int buffer_rank, int slot, int src_rank, void* host_out, int64_t count);
+int64_t exl3b_tp_debug_epoch(void);
 
 /* Count of kernels launched by this library in this process (for bench.py's gpu_launches claim). */
 int64_t exl3b_launch_count(void);
