@@ -2,6 +2,7 @@
 // TORCH_CHECKs, per-device context, kernel-path selection.  No torch types, no CPU fallback.
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "tc_common.cuh"
 #include <mutex>
 #include <string>
 #include <atomic>
@@ -174,6 +175,61 @@ int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed, cons
                                   (const half*) suh, (const half*) svh, k, n_out, packed_tiles_n, K, cb, n_offset);
 }
 
+// Path selection: auto = int8 tensor-core codebook path for mul1 at m <= 4 (like the reference, whose default for mul1 at
+// m <= 2 is its int8 GEMV, exl3_gemm.cu:182-186), else the bit-exact tcgen05 path; exl3b_set_gemm_path overrides.
+// Rows 5..8 exist on the int8 path (forced) but are not selected automatically yet: its per-unit digit warps are the
+// pacing role there (measured 25 us vs 19 us for the exact path on 4096 x 4096 at m = 8).
+static int select_gemm_path(const GemmArgs& g)
+{
+    const int path = g_force_path.load();
+    if (path == EXL3B_TAG_TC_I8)
+        EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4, or m <= 8 with m * k <= 32768)");
+    if (path == EXL3B_TAG_TC)
+        EXL3B_CHECK(gemm_tc_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: tcgen05 path forced but shape unsupported");
+    if ((path == EXL3B_TAG_TC_I8 || (path == 0 && g.m <= 4)) && gemm_tc_i8_supported(g)) return EXL3B_TAG_TC_I8;
+    if (path != EXL3B_TAG_SIMT && gemm_tc_supported(g)) return EXL3B_TAG_TC;
+    return EXL3B_TAG_SIMT;
+}
+
+int exl3b_gemm_plan(int m, int k, int n, int K, int cb, int num_sms, int force_num_sms, struct exl3b_plan* out)
+{
+    int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(out, EXL3B_ERR_ARG, "exl3_gemm_plan: null output");
+    EXL3B_CHECK(m >= 1 && k >= 128 && n >= 128, EXL3B_ERR_SHAPE, "exl3_gemm_plan: empty problem");
+    EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: k (%d) must be divisible by 128", k);
+    EXL3B_CHECK(n % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: n (%d) must be divisible by 128", n);
+    EXL3B_CHECK(num_sms >= 1, EXL3B_ERR_ARG, "exl3_gemm_plan: num_sms must be positive");
+    GemmArgs g{};
+    g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
+    const int path = select_gemm_path(g);
+    if (path < 0) return path;
+    memset(out, 0, sizeof(*out));
+    out->path = path;
+    if (path == EXL3B_TAG_SIMT) return 0;
+    TcPlan pl{};
+    const int m_pass = path == EXL3B_TAG_TC && m > 256 ? 256 : m;
+    r = path == EXL3B_TAG_TC_I8 ? plan_gemm_tc_i8(m, k, n, K, num_sms, g.max_ctas, &pl)
+                                : plan_gemm_tc(m_pass, k, n, K, num_sms, g.max_ctas, &pl);
+    if (r) return r;
+    out->passes = path == EXL3B_TAG_TC ? (m + 255) / 256 : 1;
+    out->rows = pl.rows; out->grid = pl.grid; out->stages = pl.stages; out->smem_bytes = pl.smem_total;
+    out->a_stages = pl.a_stages; out->d_bufs = pl.d_bufs; out->tmem_cols = pl.tmem_cols; out->units = pl.units;
+    return 0;
+}
+
+int exl3b_plan_unit_range(int64_t units, int grid, int cta, int64_t* begin, int64_t* end)
+{
+    EXL3B_CHECK(units >= 1 && grid >= 1 && grid <= units && cta >= 0 && cta < grid && begin && end, EXL3B_ERR_ARG, "exl3_plan_unit_range: bad argument");
+    *begin = unit_begin(units, grid, cta); *end = unit_begin(units, grid, cta + 1);
+    return 0;
+}
+
+int exl3b_plan_cta_of_unit(int64_t units, int grid, int64_t unit)
+{
+    EXL3B_CHECK(units >= 1 && grid >= 1 && grid <= units && unit >= 0 && unit < units, EXL3B_ERR_ARG, "exl3_plan_cta_of_unit: bad argument");
+    return cta_of_unit(units, grid, unit);
+}
+
 int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void* suh, void* A_had, const void* svh,
                int m, int k, int n, int K, int cb, int c_fp32, int force_shape_idx, int force_num_sms)
 {
@@ -192,19 +248,10 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
     g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f;
     g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
 
-    // path selection: auto = int8 tensor-core codebook path for mul1 at m <= 4 (like the reference, whose default for
-    // mul1 at m <= 2 is its int8 GEMV, exl3_gemm.cu:182-186), else the bit-exact tcgen05 path
-    int path = g_force_path.load();
-    if (path == EXL3B_TAG_TC_I8)
-        EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4, or m <= 8 with m * k <= 32768)");
-    if (path == EXL3B_TAG_TC)
-        EXL3B_CHECK(gemm_tc_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: tcgen05 path forced but shape unsupported");
-    // rows 5..8 exist on the int8 path (forced) but are not selected automatically yet: its per-unit digit warps are the
-    // pacing role there (measured 25 us vs 19 us for the exact path on 4096 x 4096 at m = 8)
-    if ((path == EXL3B_TAG_TC_I8 || (path == 0 && g.m <= 4)) && gemm_tc_i8_supported(g))
-        return launch_gemm_tc_i8(stream, ctx, g);
-    if (path != EXL3B_TAG_SIMT && gemm_tc_supported(g))
-        return launch_gemm_tc(stream, ctx, g);
+    int path = select_gemm_path(g);
+    if (path < 0) return path;
+    if (path == EXL3B_TAG_TC_I8) return launch_gemm_tc_i8(stream, ctx, g);
+    if (path == EXL3B_TAG_TC) return launch_gemm_tc(stream, ctx, g);
     return launch_gemm_simt(stream, ctx, g);
 }
 

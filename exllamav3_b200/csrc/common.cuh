@@ -87,6 +87,23 @@ struct GemmArgs
     float out_scale;         // extra factor folded into the output transform (mgemm weights), 1.0f otherwise
     int max_ctas;            // 0 = all SMs
 };
+// Launch geometry of one tcgen05 kernel launch: computed by the SAME functions the launchers use (plan_gemm_tc_i8 in
+// gemm_tc_i8.cu, plan_gemm_tc in gemm_tc.cu), pure host arithmetic -- exposed through exl3b_gemm_plan so that the CPU tests
+// can check budgets and the stream-K partition for shapes no GPU test runs.  Returns 0 or a negative status.
+struct TcPlan
+{
+    int rows;            // activation rows the kernel variant is built for: MR (i8 path) or NT (exact path)
+    int stages;          // shared-memory ring depth
+    int b_bytes;         // activation bytes reserved per stage
+    int b_load_bytes;    // i8: activation-cache bytes (0 = recompute per unit); exact: activation bytes copied per unit
+    int smem_total;      // dynamic shared memory of the launch
+    int grid;            // CTAs (single-matrix launch)
+    long long units;     // 128 x 128 work units
+    int a_stages, d_bufs, tmem_cols;
+};
+int plan_gemm_tc_i8(int m, int k, int n, int K, int num_sms, int max_ctas, TcPlan* pl);
+int plan_gemm_tc(int m, int k, int n, int K, int num_sms, int max_ctas, TcPlan* pl);     // m <= 256: one pass
+
 int launch_gemm_simt(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
 bool gemm_tc_supported(const GemmArgs& a);

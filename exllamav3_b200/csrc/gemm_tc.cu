@@ -551,6 +551,37 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
     return 0;
 }
 
+// launch geometry of one pass (m <= 256 rows), also behind exl3b_gemm_plan
+int plan_gemm_tc(int m, int k, int n, int K, int num_sms, int max_ctas, TcPlan* pl)
+{
+    EXL3B_CHECK(m >= 1 && m <= 256, EXL3B_ERR_ARG, "plan_gemm_tc: one pass handles 1..256 rows");
+    const int NT = (m + 15) / 16 * 16;
+    const bool fused_x = m <= 8;
+    // all of TMEM: the operand-stage loop (decode -> tcgen05.st -> MMA -> commit -> decode) has ~1.3 us of latency;
+    // the number of 64-column A stages in flight is what hides it (measured: 3 stages = 450 ns per unit floor)
+    pl->tmem_cols = 512;
+    pl->a_stages = NT <= 32 ? 7 : 4;
+    pl->d_bufs = NT <= 128 ? 2 : 1;
+    pl->b_load_bytes = m <= 8 ? 2048 : NT * 256;
+    const int b_bytes = fused_x ? 2048 : NT * 256;       // m <= 8: only the first row group is ever written / needed
+    const int stage_bytes = 2048 * K + b_bytes;
+    const int budget = 200 * 1024;
+    int stages = budget / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) stages = 2;
+    const TcSmemLayout L = tc_smem_layout(K, b_bytes, stages);
+    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: shared-memory budget exceeded");
+    const long long U = (long long) (k / 128) * (n / 128);
+    int grid = num_sms;
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (grid > U) grid = (int) U;
+    EXL3B_CHECK((size_t) 2 * grid * NT * 128 * 4 <= DevCtx::WS_BYTES_PER_SLOT, EXL3B_ERR_UNSUPPORTED,
+                "exl3_gemm: split-K workspace too small");
+    EXL3B_CHECK(n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+    pl->rows = NT; pl->stages = stages; pl->b_bytes = b_bytes; pl->smem_total = L.total; pl->grid = grid; pl->units = U;
+    return 0;
+}
+
 int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 {
     const size_t esz = a.c_fp32 ? 4 : 2;
@@ -559,7 +590,9 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     for (int m0 = 0; m0 < a.m; m0 += 256)
     {
         const int m = a.m - m0 < 256 ? a.m - m0 : 256;
-        const int NT = (m + 15) / 16 * 16;
+        TcPlan pl;
+        { int r = plan_gemm_tc(m, a.k, a.n, a.K, ctx->num_sms, a.max_ctas, &pl); if (r) return r; }
+        const int NT = pl.rows;
         const int slot = ctx->next_slot();
         const bool fused_x = m <= 8;
         uint8_t* xh_tiled = nullptr;
@@ -575,38 +608,19 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         p.xh_tiled = xh_tiled; p.B = a.B; p.C = (char*) a.C + (size_t) m0 * a.n * esz; p.svh = a.svh;
         p.m = m; p.k = a.k; p.n = a.n; p.NT = NT; p.c_fp32 = a.c_fp32; p.out_scale = a.out_scale;
         p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
-        const bool small = NT <= 32;
-        // all of TMEM: the operand-stage loop (decode -> tcgen05.st -> MMA -> commit -> decode) has ~1.3 us of latency;
-        // the number of 64-column A stages in flight is what hides it (measured: 3 stages = 450 ns per unit floor)
-        p.tmem_cols = 512;
-        p.a_stages = NT <= 32 ? 7 : 4;
-        p.d_bufs = NT <= 128 ? 2 : 1;
-        p.b_load_bytes = m <= 8 ? 2048 : NT * 256;
-        const int b_bytes = fused_x ? 2048 : NT * 256;       // m <= 8: only the first row group is ever written / needed
-        const int stage_bytes = 2048 * a.K + b_bytes;
-        const int budget = 200 * 1024;
-        int stages = budget / stage_bytes;
-        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-        if (stages < 2) stages = 2;
-        p.stages = stages;
+        p.tmem_cols = pl.tmem_cols;
+        p.a_stages = pl.a_stages;
+        p.d_bufs = pl.d_bufs;
+        p.b_load_bytes = pl.b_load_bytes;
+        p.stages = pl.stages;
         p.dbg = g_tc_dbg;
         p.knob_ = g_tc_knob;
         p.A_raw = fused_x ? a.A + (size_t) m0 * a.k : nullptr;
         p.suh = a.suh;
-        p.b_bytes = b_bytes;
-        const TcSmemLayout L = tc_smem_layout(a.K, b_bytes, stages);
-        EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: shared-memory budget exceeded");
-
-        const long long U = (long long) (a.k / 128) * (a.n / 128);
-        int grid = ctx->num_sms;
-        if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
-        if (grid > U) grid = (int) U;
-        EXL3B_CHECK((size_t) 2 * grid * NT * 128 * 4 <= DevCtx::WS_BYTES_PER_SLOT, EXL3B_ERR_UNSUPPORTED,
-                    "exl3_gemm: split-K workspace too small");
-        EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+        p.b_bytes = pl.b_bytes;
 
         cudaError_t err = cudaSuccess;
-        EXL3B_DISPATCH_K_CB(tc_launch_v, a.K, a.cb, stream, grid, L.total, p, tmap, &err);
+        EXL3B_DISPATCH_K_CB(tc_launch_v, a.K, a.cb, stream, pl.grid, pl.smem_total, p, tmap, &err);
         count_launch();
         EXL3B_CUDA(err);
     }

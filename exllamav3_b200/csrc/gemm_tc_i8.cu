@@ -47,43 +47,55 @@ bool gemm_tc_i8_supported(const GemmArgs& a)
     return a.cb == 2 && i8_rows_ok(a.m, a.k) && a.k >= 128 && a.n >= 128 && a.k % 128 == 0 && a.n % 128 == 0;
 }
 
+// launch geometry (also behind exl3b_gemm_plan): rows variant, ring depth, activation cache, grid
+int plan_gemm_tc_i8(int m, int k, int n, int K, int num_sms, int max_ctas, TcPlan* pl)
+{
+    const int MR = m <= 4 ? 4 : 8;
+    const int stage_bytes = 2048 * K + i8_b_stage(MR);
+    int cache_bytes = m * k * 2;
+    cache_bytes = (cache_bytes + 127) / 128 * 128;
+    if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
+    int stages = (200 * 1024 - cache_bytes) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) stages = 2;
+    const TcSmemLayout L = i8_smem_layout(K, MR, stages, cache_bytes);
+    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): shared-memory budget exceeded");
+    const long long U = (long long) (k / 128) * (n / 128);
+    int grid = num_sms;
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (grid > U) grid = (int) U;
+    EXL3B_CHECK(n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+    EXL3B_CHECK(grid <= DevCtx::I8_PART_CTAS, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): grid exceeds the split-K exchange buffer");
+    pl->rows = MR; pl->stages = stages; pl->b_bytes = i8_b_stage(MR); pl->b_load_bytes = cache_bytes; pl->smem_total = L.total;
+    pl->grid = grid; pl->units = U; pl->a_stages = I8_A_STAGES; pl->d_bufs = 2; pl->tmem_cols = 512;
+    return 0;
+}
+
 int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 {
     CUtensorMap tmap;
     { int r = get_weight_tmap(a.B, a.k, a.n, a.K, &tmap); if (r) return r; }
+    TcPlan pl;
+    { int r = plan_gemm_tc_i8(a.m, a.k, a.n, a.K, ctx->num_sms, a.max_ctas, &pl); if (r) return r; }
     const int slot = ctx->next_slot();
     TcParams p{};
     p.B = a.B; p.C = a.C; p.svh = a.svh; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
     p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
     p.parts = ctx->i8_parts_slot(slot);
-    const int MR = a.m <= 4 ? 4 : 8;
-    const int stage_bytes = 2048 * a.K + i8_b_stage(MR);
-    int cache_bytes = a.m * a.k * 2;
-    cache_bytes = (cache_bytes + 127) / 128 * 128;
-    if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
-    int stages = (200 * 1024 - cache_bytes) / stage_bytes;
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (stages < 2) stages = 2;
-    p.stages = stages; p.b_bytes = i8_b_stage(MR); p.b_load_bytes = cache_bytes;
-    const TcSmemLayout L = i8_smem_layout(a.K, MR, stages, cache_bytes);
-    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm (i8): shared-memory budget exceeded");
-    const long long U = (long long) (a.k / 128) * (a.n / 128);
-    int grid = ctx->num_sms;
-    if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
-    if (grid > U) grid = (int) U;
-    EXL3B_CHECK(a.n / 128 <= DevCtx::COUNTERS_PER_SLOT, EXL3B_ERR_UNSUPPORTED, "exl3_gemm: too many column strips");
+    p.stages = pl.stages; p.b_bytes = pl.b_bytes; p.b_load_bytes = pl.b_load_bytes;
+    const int grid = pl.grid, smem_total = pl.smem_total;
     cudaError_t err = cudaSuccess;
     switch (a.K)
     {
-        case 1: err = i8_launch<1>(stream, grid, L.total, p, tmap); break;
-        case 2: err = i8_launch<2>(stream, grid, L.total, p, tmap); break;
-        case 3: err = i8_launch<3>(stream, grid, L.total, p, tmap); break;
-        case 4: err = i8_launch<4>(stream, grid, L.total, p, tmap); break;
-        case 5: err = i8_launch<5>(stream, grid, L.total, p, tmap); break;
-        case 6: err = i8_launch<6>(stream, grid, L.total, p, tmap); break;
-        case 7: err = i8_launch<7>(stream, grid, L.total, p, tmap); break;
-        case 8: err = i8_launch<8>(stream, grid, L.total, p, tmap); break;
+        case 1: err = i8_launch<1>(stream, grid, smem_total, p, tmap); break;
+        case 2: err = i8_launch<2>(stream, grid, smem_total, p, tmap); break;
+        case 3: err = i8_launch<3>(stream, grid, smem_total, p, tmap); break;
+        case 4: err = i8_launch<4>(stream, grid, smem_total, p, tmap); break;
+        case 5: err = i8_launch<5>(stream, grid, smem_total, p, tmap); break;
+        case 6: err = i8_launch<6>(stream, grid, smem_total, p, tmap); break;
+        case 7: err = i8_launch<7>(stream, grid, smem_total, p, tmap); break;
+        case 8: err = i8_launch<8>(stream, grid, smem_total, p, tmap); break;
     }
     count_launch();
     EXL3B_CUDA(err);

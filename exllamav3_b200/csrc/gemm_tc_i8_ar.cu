@@ -228,7 +228,7 @@ static cudaError_t i8_ar_launch(cudaStream_t stream, int grid, int smem_bytes, c
     return cudaLaunchKernelEx(&cfg, gemm_tc_i8_ar_kernel<K>, p, tmap, ar);
 }
 
-// Same launch geometry as launch_gemm_tc_i8 (gemm_tc_i8.cu) for MR = 4; every rank must issue the same sequence of
+// Same launch geometry as launch_gemm_tc_i8 (plan_gemm_tc_i8, gemm_tc_i8.cu); every rank must issue the same sequence of
 // row-parallel calls (the requirement any collective has).
 int launch_gemm_tc_i8_ar(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
 {
@@ -244,35 +244,24 @@ int launch_gemm_tc_i8_ar(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     p.out_scale = a.out_scale; p.ws = ctx->ws_slot(slot); p.counters = ctx->counter_slot(slot);
     p.A_raw = a.A; p.suh = a.suh; p.dbg = g_tc_dbg; p.knob_ = g_tc_knob;
     p.parts = ctx->i8_parts_slot(slot);
-    constexpr int MR = 4;
-    const int stage_bytes = 2048 * a.K + i8_b_stage(MR);
-    int cache_bytes = a.m * a.k * 2;
-    cache_bytes = (cache_bytes + 127) / 128 * 128;
-    if (cache_bytes > I8_CACHE_MAX_BYTES) cache_bytes = 0;
-    int stages = (200 * 1024 - cache_bytes) / stage_bytes;
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (stages < 2) stages = 2;
-    p.stages = stages; p.b_bytes = i8_b_stage(MR); p.b_load_bytes = cache_bytes;
-    const TcSmemLayout L = i8_smem_layout(a.K, MR, stages, cache_bytes);
-    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_gemm_allreduce: shared-memory budget exceeded");
-    const long long U = (long long) (a.k / 128) * (a.n / 128);
-    int grid = ctx->num_sms;
-    if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
-    if (grid > U) grid = (int) U;
+    TcPlan pl;
+    { int r = plan_gemm_tc_i8(a.m, a.k, a.n, a.K, ctx->num_sms, a.max_ctas, &pl); if (r) return r; }      // m <= 4: the MR = 4 variant
+    p.stages = pl.stages; p.b_bytes = pl.b_bytes; p.b_load_bytes = pl.b_load_bytes;
+    const int grid = pl.grid;
     ArArgs ar{};
     for (int j = 0; j < g->world; ++j) ar.recv[j] = g->recv[j];
     ar.state = g->state; ar.slot_elems = g->slot_elems; ar.rank = g->rank; ar.world = g->world;
     cudaError_t err = cudaSuccess;
     switch (a.K)
     {
-        case 1: err = i8_ar_launch<1>(stream, grid, L.total, p, tmap, ar); break;
-        case 2: err = i8_ar_launch<2>(stream, grid, L.total, p, tmap, ar); break;
-        case 3: err = i8_ar_launch<3>(stream, grid, L.total, p, tmap, ar); break;
-        case 4: err = i8_ar_launch<4>(stream, grid, L.total, p, tmap, ar); break;
-        case 5: err = i8_ar_launch<5>(stream, grid, L.total, p, tmap, ar); break;
-        case 6: err = i8_ar_launch<6>(stream, grid, L.total, p, tmap, ar); break;
-        case 7: err = i8_ar_launch<7>(stream, grid, L.total, p, tmap, ar); break;
-        case 8: err = i8_ar_launch<8>(stream, grid, L.total, p, tmap, ar); break;
+        case 1: err = i8_ar_launch<1>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 2: err = i8_ar_launch<2>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 3: err = i8_ar_launch<3>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 4: err = i8_ar_launch<4>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 5: err = i8_ar_launch<5>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 6: err = i8_ar_launch<6>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 7: err = i8_ar_launch<7>(stream, grid, pl.smem_total, p, tmap, ar); break;
+        case 8: err = i8_ar_launch<8>(stream, grid, pl.smem_total, p, tmap, ar); break;
     }
     count_launch();
     EXL3B_CUDA(err);

@@ -79,8 +79,9 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int K, int b_bytes, int s
 }
 
 // ---- work partition helpers -------------------------------------------------------------------------------------
-__device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
-__device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
+// (host + device: the CPU tests walk the same partition the kernels use, exl3b_plan_* in api.cu)
+__host__ __device__ __forceinline__ long long unit_begin(long long U, int G, int c) { return U * c / G; }
+__host__ __device__ __forceinline__ int cta_of_unit(long long U, int G, long long g) { return (int) (((g + 1) * G - 1) / U); }
 
 
 // Load the K+1 words (chunk + preceding word, the latter by shuffle from the neighbouring lane) of four tiles

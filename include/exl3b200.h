@@ -63,6 +63,30 @@ int exl3b_cc(int device);
 int exl3b_set_gemm_path(int tag);
 
 /*
+ * Launch-geometry introspection -- the counterpart of ext.exl3_gemm_num_kernel_shapes / ext.exl3_gemm_shape_compat
+ * (exllamav3_ext/bindings.cpp:128-129, exllamav3_ext/quant/exl3_kernel_map.cu:23-75): which kernel path a call takes and with
+ * what persistent grid, shared-memory ring and TMEM staging, computed by the same host functions the launchers use.  Pure
+ * host arithmetic: needs no device (num_sms is an argument), so shapes can be vetted without a GPU.
+ * exl3b_plan_unit_range / exl3b_plan_cta_of_unit expose the stream-K partition of `units` 128x128 work units (k fastest)
+ * over `grid` CTAs: CTA c owns [units*c/grid, units*(c+1)/grid).
+ */
+struct exl3b_plan
+{
+    int32_t path;        /* EXL3B_TAG_*                                                                  */
+    int32_t passes;      /* launches of the GEMM kernel (exact path: ceil(m / 256))                      */
+    int32_t rows;        /* rows the kernel variant is built for (i8 path: 4 or 8; exact path: m rounded up to 16) */
+    int32_t grid;        /* CTAs                                                                         */
+    int32_t stages;      /* shared-memory ring depth                                                     */
+    int32_t smem_bytes;  /* dynamic shared memory per CTA                                                */
+    int32_t a_stages, d_bufs, tmem_cols;     /* TMEM operand stages / accumulator buffers / columns      */
+    int32_t reserved;
+    int64_t units;       /* 128 x 128 work units                                                         */
+};
+int exl3b_gemm_plan(int m, int k, int n, int K, int cb, int num_sms, int force_num_sms, struct exl3b_plan* out);
+int exl3b_plan_unit_range(int64_t units, int grid, int cta, int64_t* begin, int64_t* end);
+int exl3b_plan_cta_of_unit(int64_t units, int grid, int64_t unit);
+
+/*
  * exl3b_gemm -- replaces ext.exl3_gemm (exllamav3_ext/bindings.cpp:126, exllamav3_ext/quant/exl3_gemm.cuh:21-33,
  * implementation exllamav3_ext/quant/exl3_gemm.cu:110-309).
  *
