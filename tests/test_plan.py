@@ -35,7 +35,7 @@ def lib():
     L.exl3b_plan_unit_range.restype = ctypes.c_int
     L.exl3b_plan_cta_of_unit.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64]
     L.exl3b_plan_cta_of_unit.restype = ctypes.c_int
-    assert ext.set_gemm_path(0) == 0
+    ext.set_gemm_path(0)
     return L
 
 

@@ -61,6 +61,47 @@ def test_tp_column_and_row_sharding_world2():
         assert err_r < 2e-3, err_r            # fp16 rounding of xh is per 128-block => partial sums differ only in fp64 order
 
 
+def _worker_rank_ordered(rank, world, port, ret):
+    """The fused row-parallel epilogue's arithmetic (gemm_tc_i8_body.cuh emit_rows, AR = true), restated on the host: every
+    rank holds every rank's finished fp32 partial and adds them in RANK order, so all ranks end with bit-identical sums."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from exllamav3_b200 import LinearEXL3, tp
+        from oracle import exl3_oracle as orc
+        k, n, K, cb, m = 768, 512, 4, 2, 2
+        tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
+        lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr),
+                         mul1=torch.zeros((), dtype=torch.int))
+        rs = tp.row_shard(lin, rank, world)
+        first, last = tp.split_ranges(k, world)[rank]
+        part = torch.from_numpy(orc.exl3_gemm_f64(np.ascontiguousarray(x[:, first:last]), rs.trellis.numpy(), rs.suh.numpy(),
+                                                  rs.svh.numpy(), rs.K, cb)).float()           # the rank's fp32 partial
+        slots = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(slots, part)                                   # = every peer storing into slot [its rank]
+        acc = torch.zeros_like(part)
+        for j in range(world):
+            acc = acc + (part if j == rank else slots[j])             # rank order, own partial from registers
+        ref = torch.from_numpy(orc.exl3_gemm_f64(x, tr, suh, svh, K, cb))
+        everyone = [torch.empty_like(acc) for _ in range(world)]
+        dist.all_gather(everyone, acc)
+        ret[rank] = (float((acc.double() - ref).abs().max() / ref.abs().max()), all(torch.equal(everyone[0], e) for e in everyone))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_rank_ordered_sum_is_identical_on_all_ranks_world3():
+    world, port = 3, 29917 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_rank_ordered, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        err, identical = ret[rank]
+        assert err < 2e-3 and identical
+
+
 def test_split_ranges():
     from exllamav3_b200 import tp
     assert tp.split_ranges(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
