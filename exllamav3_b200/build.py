@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexl3b200.so")
 
-SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "gemm_tc_i8_ar.cu", "hgemm.cu", "hgemm_tc.cu"]
+SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "gemm_tc_i8_ar.cu", "gemm_tc_i8_routed.cu", "hgemm.cu", "hgemm_tc.cu"]
 HEADERS = ["common.cuh", "decode.cuh", "epilogue.cuh", "ptx.cuh", "tc_common.cuh", "gemm_tc_i8_body.cuh", os.path.join("..", "..", "include", "exl3b200.h")]
 
 NVCC_FLAGS = [

@@ -181,7 +181,8 @@ int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed, cons
 // pacing role there (measured 25 us vs 19 us for the exact path on 4096 x 4096 at m = 8).
 static int select_gemm_path(const GemmArgs& g)
 {
-    const int path = g_force_path.load();
+    int path = g_force_path.load();
+    if (path == EXL3B_TAG_TC_I8_ROUTED) path = 0;            // only concerns exl3b_mgemm
     if (path == EXL3B_TAG_TC_I8)
         EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4, or m <= 8 with m * k <= 32768)");
     if (path == EXL3B_TAG_TC)
@@ -329,8 +330,11 @@ int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, co
     a.c_fp32 = c_fp32 != 0; a.min_index = min_index; a.max_index = max_index; a.num_tokens = num_tokens;
     a.size_n_list = size_n_list; a.c_ptrs = c_ptrs; a.num_c_ptrs = num_c_ptrs;
     const int path = g_force_path.load();
-    if ((path == EXL3B_TAG_TC_I8 || (path == 0 && m <= 4)) && mgemm_tc_i8_supported(ctx, a))
+    if ((path == EXL3B_TAG_TC_I8 || path == EXL3B_TAG_TC_I8_ROUTED || (path == 0 && m <= 4)) && mgemm_tc_i8_supported(ctx, a))
         return launch_mgemm_tc_i8((cudaStream_t) stream, ctx, a);
+    // routed / weighted calls (MoE decode) on the tensor-core path: opt-in until verified on hardware
+    if (path == EXL3B_TAG_TC_I8_ROUTED && mgemm_tc_i8_routed_supported(ctx, a))
+        return launch_mgemm_tc_i8_routed((cudaStream_t) stream, ctx, a);
     return launch_mgemm((cudaStream_t) stream, ctx, a);
 }
 

@@ -134,6 +134,11 @@ struct MGemmArgs
     const int32_t* size_n_list; const uint64_t* c_ptrs; int num_c_ptrs;
 };
 int launch_mgemm(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
+int launch_mgemm_resolve(cudaStream_t stream, MSlotTable* tab, const MGemmArgs& a, int bszm);
+int launch_mgemm_reduce(cudaStream_t stream, DevCtx* ctx, const MSlotTable* tab, const MGemmArgs& a);
+// routed / weighted exl3_mgemm (MoE decode) on the tcgen05 int8 path (gemm_tc_i8_routed.cu): opt-in, tag EXL3B_TAG_TC_I8_ROUTED
+bool mgemm_tc_i8_routed_supported(const DevCtx* ctx, const MGemmArgs& a);
+int launch_mgemm_tc_i8_routed(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
 
 int launch_hgemm(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,
                  int64_t c_stride);

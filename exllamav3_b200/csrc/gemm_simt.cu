@@ -292,6 +292,27 @@ __global__ void mgemm_reduce_kernel(void* C, const MSlotTable* tab, int m, int n
     }
 }
 
+// The two bookkeeping stages of exl3_mgemm as stand-alone launches, for the tcgen05 routed path (gemm_tc_i8_routed.cu), which
+// replaces only the contraction in between.
+int launch_mgemm_resolve(cudaStream_t stream, MSlotTable* tab, const MGemmArgs& a, int bszm)
+{
+    mgemm_resolve_kernel<<<1, 32, 0, stream>>>(tab, a.indices, a.weights, bszm, a.min_index, a.max_index);
+    count_launch();
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return 0;
+}
+
+int launch_mgemm_reduce(cudaStream_t stream, DevCtx* ctx, const MSlotTable* tab, const MGemmArgs& a)
+{
+    size_t mn = (size_t) a.m * a.n;
+    int grid = (int) ((mn + 255) / 256);
+    if (grid > 4 * ctx->num_sms) grid = 4 * ctx->num_sms;
+    mgemm_reduce_kernel<<<grid, 256, 0, stream>>>(a.C, tab, a.m, a.n, a.c_fp32, a.num_tokens);
+    count_launch();
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return 0;
+}
+
 int launch_mgemm(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
 {
     int bszm_in = a.bszm_in, bszm_out = a.bszm_out;

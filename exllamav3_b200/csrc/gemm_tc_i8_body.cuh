@@ -66,8 +66,12 @@ __host__ __device__ inline TcSmemLayout i8_smem_layout(int K, int MR, int stages
 
 // The kernel body, shared by the plain kernel (gemm_tc_i8.cu) and the row-parallel variant whose epilogue sums the
 // tensor-parallel partial outputs over NVLink peer memory (gemm_tc_i8_ar.cu, AR = true).
-template <int K, int MR, bool AR>
-__device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtensorMap* tmap_w, const ArArgs* ar)
+// ROUTED = true (gemm_tc_i8_routed.cu): multi-matrix launch whose CTA groups are the ACTIVE SLOTS of an exl3_mgemm call with
+// indices / weights / expert-range filter (MoE decode); slot -> matrix and the slot's output weight come from the table the
+// resolve kernel wrote just before this launch.
+template <int K, int MR, bool AR, bool ROUTED = false>
+__device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtensorMap* tmap_w, const ArArgs* ar,
+                                                const RouteArgs* route = nullptr)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int I8_B_BYTES = i8_b_bytes(MR);
@@ -85,11 +89,24 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     const bool multi = p.num_mats > 0;
     float* const parts = p.parts;                    // split-K exchange buffer, one slot of MR x 128 floats per CTA of the grid
     int cta0 = 0;                                    // first CTA of this matrix's group
+    [[maybe_unused]] float routed_scale = 1.f;
     if (multi)
     {
         G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G;
+        const int slot = mat;                        // inputs / outputs are per slot, the pointer tables per matrix
+        if constexpr (ROUTED)
+        {
+            // the slot table is written by the resolve kernel that precedes this launch: nothing can start before it is
+            // complete (the weight prefetch of the plain kernel is given up here).  Slots beyond the active ones, and
+            // skipped slots (negative index), have no work: the whole CTA group leaves before it allocates anything.
+            pdl_wait();
+            if (slot >= route->tab->n_active) return;
+            mat = route->tab->mat[slot];
+            if (mat < 0) return;
+            if (route->has_weights) routed_scale = __half2float(route->tab->weight[slot]);
+        }
         suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
-        A_raw += (size_t) mat * p.a_mat_stride; Cout += (size_t) mat * p.c_mat_stride;
+        A_raw += (size_t) slot * p.a_mat_stride; Cout += (size_t) slot * p.c_mat_stride;
     }
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -550,7 +567,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
             {
                 for (int r = q; r < p.m; r += 4)
                     output_row_128(tile + r * 128, Cout, (size_t) r * p.n + strip * 128,
-                                   svh ? svh + strip * 128 : nullptr, p.out_scale, p.c_fp32 != 0, lane);
+                                   svh ? svh + strip * 128 : nullptr, ROUTED ? routed_scale : p.out_scale, p.c_fp32 != 0, lane);
             }
             else
             {
@@ -568,7 +585,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                 for (int r = q; r < p.m; r += 4)
                 {
                     float v[4];
-                    finish_row_128_f32(tile + r * 128, svh ? svh + strip * 128 : nullptr, p.out_scale, lane, v);
+                    finish_row_128_f32(tile + r * 128, svh ? svh + strip * 128 : nullptr, ROUTED ? routed_scale : p.out_scale, lane, v);
                     const long long e0 = (long long) r * p.n + strip * 128 + lane * 4;
                     uint4 mine = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
                     if (mine.x == I8_SENTINEL) mine.x = 0x7fc00000u;            // a NaN stays a NaN

@@ -61,6 +61,13 @@ struct ArArgs
     int rank, world;
 };
 
+// Routed multi-matrix launch (exl3_mgemm with indices / weights / expert-range filter): the active-slot table of the call
+struct RouteArgs
+{
+    const MSlotTable* tab;       // written by mgemm_resolve_kernel earlier on the same stream
+    int has_weights;             // multiply each slot's output by tab->weight[slot]
+};
+
 struct TcSmemLayout
 {
     int w_bytes, b_bytes, off_b, off_tile, off_bars, total;

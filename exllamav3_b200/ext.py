@@ -69,6 +69,7 @@ EXL3B_TAG_SIMT = 100
 EXL3B_TAG_TC = 200
 EXL3B_TAG_TC_I8 = 210
 EXL3B_TAG_TC_I8_AR = 211
+EXL3B_TAG_TC_I8_ROUTED = 212
 TP_HANDLE_BYTES = 64
 
 lib = _lib      # raw handle for bench.py / tests (symbol export checks)

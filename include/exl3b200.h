@@ -46,6 +46,7 @@ enum exl3b_status
 #define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
 #define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
 #define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path: mul1, m <= 4 (auto); m <= 8 with m*k <= 32768 when forced */
+#define EXL3B_TAG_TC_I8_ROUTED 212 /* routed / weighted exl3b_mgemm (MoE decode) on the kind::i8 kernel; taken only when forced (opt-in) */
 #define EXL3B_TAG_TC_I8_AR 211 /* the same kernel with the tensor-parallel sum fused into its epilogue (exl3b_gemm_allreduce) */
 
 int exl3b_abi_version(void);
@@ -58,7 +59,8 @@ const char* exl3b_last_error(void);
 int exl3b_num_sms(int device);
 int exl3b_cc(int device);
 
-/* Force a kernel path for exl3b_gemm on this process: 0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC, EXL3B_TAG_TC_I8.
+/* Force a kernel path for exl3b_gemm on this process: 0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC, EXL3B_TAG_TC_I8;
+   EXL3B_TAG_TC_I8_ROUTED: exl3b_gemm as auto, exl3b_mgemm with indices / weights on the tensor-core path where eligible.
    (The reference exposes force_shape_idx / force_num_sms per call for the same purpose.) Returns previous value. */
 int exl3b_set_gemm_path(int tag);
 

@@ -20,7 +20,9 @@ fi
 timeout 900 python -m pytest tests -q -m gpu -x > "$out/gpu_suite.log" 2>&1;  echo "gpu suite rc=$?" | tee "$out/summary.txt"
 EXL3B_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_tp_fused.py -q -m gpu > "$out/unverified.log" 2>&1
 echo "unverified (fused all-reduce: world 1, loop-back) rc=$?" | tee -a "$out/summary.txt"
+EXL3B_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_moe_routed.py -q -m gpu > "$out/unverified_moe.log" 2>&1
+echo "unverified (routed int8 mgemm) rc=$?" | tee -a "$out/summary.txt"
 timeout 600 python bench.py > "$out/bench_n1.json" 2> "$out/bench_n1.err";         echo "bench rc=$?" | tee -a "$out/summary.txt"
 timeout 300 python __graft_entry__.py --smoke > "$out/smoke.log" 2>&1;             echo "smoke rc=$?" | tee -a "$out/summary.txt"
-tail -3 "$out/gpu_suite.log" "$out/unverified.log"
+tail -3 "$out/gpu_suite.log" "$out/unverified.log" "$out/unverified_moe.log"
 cat "$out/bench_n1.json"
