@@ -14,11 +14,14 @@
 //
 //   Output order matches what a tcgen05 K-major operand row wants: out[j] = packed fp16 pair (k = 2j, 2j+1).
 #pragma once
-#include <cuda_fp16.h>
 #include <stdint.h>
+#ifndef EXL3B_HOST_EMU
+#include <cuda_fp16.h>
+#endif
 
 namespace exl3b {
 
+#ifndef EXL3B_HOST_EMU
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
     uint32_t r;
@@ -46,6 +49,27 @@ __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+#else
+// Host restatement of the four PTX instructions above (and of __funnelshift_r / __dp4a, provided by the including file) so
+// that the SAME decode templates below compile with g++ and can be checked against the oracle without a GPU
+// (tests/emu/decode_emu.cpp, tests/test_decode_emu.py).  Never part of the library.
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t src = ((uint64_t) b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i)
+    {
+        const uint32_t s = (sel >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t) (src >> (8 * (s & 7))) & 0xff;
+        if (s & 8) byte = (byte & 0x80) ? 0xff : 0x00;            // sign-replicate mode of prmt.b32
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+inline uint32_t lop3_and_xor(uint32_t x, uint32_t b, uint32_t c) { return (x & b) ^ c; }
+inline uint32_t hadd2_u32(uint32_t a, uint32_t b) { return exl3b_emu_f16x2_fma(a, 0x3c003c00u, b); }            // a * 1 + b, one rounding
+inline uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c) { return exl3b_emu_f16x2_fma(a, b, c); }
+#endif
 
 // Two 16-bit states -> packed fp16x2 (lo = value(s0), hi = value(s1)), bit-exact with the reference's
 // decode_3inst_2<cb> (codebook.cuh:92-123).
