@@ -184,6 +184,23 @@ __device__ __forceinline__ void decode16_i8(const uint32_t (&w)[K + 1], uint32_t
     products4<K, HALF, 3>(w, out[6], out[7], out[14], out[15]);
 }
 
+// K = 4 with the half as a RUN-TIME (warp-uniform) value: span_shift = 16 (half 0) or 0 (half 1) selects the 32-bit span
+// holding the group's four windows with one funnel shift, so both halves run the same instruction stream and the
+// per-tile branch of the kernels' decode loop disappears (experiment switch EXL3B_I8_K4_BRANCHFREE in gemm_tc_i8_body.cuh;
+// checked against the oracle on the host by tests/test_decode_emu.py).
+__device__ __forceinline__ void decode16_i8_k4_rt(const uint32_t (&w)[5], uint32_t span_shift, uint32_t (&out)[16])
+{
+    #pragma unroll
+    for (int J = 0; J < 4; ++J)
+    {
+        const uint32_t v = __funnelshift_r(w[1 + J], w[J], span_shift);       // (w[J] : w[1+J]) >> 16, or w[1+J] itself
+        const uint32_t t = v >> 4;
+        const uint32_t s3 = prmt(v, 0u, 0x4410), s1 = prmt(v, 0u, 0x4421), s2 = prmt(t, 0u, 0x4410), s0 = prmt(t, 0u, 0x4421);
+        out[2 * J] = s0 * 0x83DCD12Du; out[2 * J + 1] = s1 * 0x83DCD12Du;
+        out[2 * J + 8] = s2 * 0x83DCD12Du; out[2 * J + 9] = s3 * 0x83DCD12Du;
+    }
+}
+
 // Thread -> column mapping inside a 128-column strip (8 tiles).  q = lane quarter (warp index % 4), i = lane.
 //   tile-in-strip = 4*(q>>1) + (i>>3), chunk = i&7, half = q&1   =>   n_local = 16*tile + 8*half + chunk
 __device__ __forceinline__ int strip_tile(int q, int i)  { return 4 * (q >> 1) + (i >> 3); }

@@ -38,6 +38,16 @@ namespace exl3b {
 
 using namespace ptx;
 
+// Experiment switch (round 2, to be timed on hardware): K = 4 decode without the per-tile half branch (decode16_i8_k4_rt).
+// Arithmetic verified on the host (tests/test_decode_emu.py).  Static effect on gemm_tc_i8_kernel<4, 4> (cuobjdump, 12.9):
+// the decode loop body shrinks from ~370 to ~320 SASS lines (one SHF more per four weights on the half-1 warps, the
+// per-tile branch / reconvergence instructions gone), but ptxas then overlaps the four tiles of a unit (64 product
+// registers live), goes from 72 to 80 registers and spills ~10 loop-carried words per unit -- whether that is a net win is
+// a measurement, not a guess.  Off: the shipped kernels are unchanged (SASS identical).
+#ifndef EXL3B_I8_K4_BRANCHFREE
+#define EXL3B_I8_K4_BRANCHFREE 0
+#endif
+
 constexpr int I8_MAX_M = 8;                                    // rows per launch: kernel instantiated for MR = 4 and MR = 8 rows
 constexpr int I8_A_STAGE_COLS = 128;
 constexpr int I8_A_STAGES = 3;
@@ -497,6 +507,9 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                     #pragma unroll
                     for (int i = 0; i < 16; ++i) o[i] = w[j][i % (K + 1)];
                 }
+#if EXL3B_I8_K4_BRANCHFREE
+                else if constexpr (K == 4) decode16_i8_k4_rt(w[j], (q & 1) ? 0u : 16u, o);
+#endif
                 else if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
                 if (!(KNOB & 2))
                     tmem_st_32x32b_x16(tmem_base + lane_base + as * I8_A_STAGE_COLS + 16 * t, o);

@@ -76,6 +76,15 @@ int emu_load_chunk(int K, const uint32_t* tile, int chunk, uint32_t* w) { FOR_K(
 int emu_decode16(int K, int cb, int half, const uint32_t* w, uint32_t* out8) { if (cb < 0 || cb > 2) return -1; FOR_K(dec16_cb, cb, half, w, out8); return 0; }
 // the same column as 16 raw products state * 0x83DCD12D in k order: int8 tensor-core path (gemm_tc_i8_body.cuh)
 int emu_decode16_i8(int K, int half, const uint32_t* w, uint32_t* out16) { FOR_K(dec16_i8, half, w, out16); return 0; }
+// K = 4 with a run-time half (branch-free experiment)
+int emu_decode16_i8_k4_rt(int half, const uint32_t* w, uint32_t* out16)
+{
+    uint32_t ww[5], o[16];
+    for (int i = 0; i < 5; ++i) ww[i] = w[i];
+    decode16_i8_k4_rt(ww, half ? 0u : 16u, o);
+    for (int i = 0; i < 16; ++i) out16[i] = o[i];
+    return 0;
+}
 // thread -> column mapping inside a 128-column strip
 int emu_strip_col(int q, int lane) { return strip_col(q, lane); }
 

@@ -96,6 +96,21 @@ def test_decode16_i8_products_and_byte_sums(emu, K):
                 assert (np.abs(full - vals_ref[t, :, n]) <= 2.0 ** -11 * np.maximum(np.abs(full), 2.0 ** -14) + 1e-12).all()
 
 
+def test_branch_free_k4_decode_equals_the_templated_one(emu):
+    """decode16_i8_k4_rt (half as a run-time span shift, one funnel shift per four weights) == decode16_i8<4, half>."""
+    emu.emu_decode16_i8_k4_rt.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+    rng = np.random.default_rng(7)
+    for it in range(2000):
+        w = rng.integers(0, 2 ** 32, size=5, dtype=np.uint64).astype(np.uint32)
+        if it == 0: w[:] = 0
+        if it == 1: w[:] = 0xffffffff
+        for half in range(2):
+            a = np.zeros(16, dtype=np.uint32); b = np.zeros(16, dtype=np.uint32)
+            emu.emu_decode16_i8(4, half, _p(w), _p(a))
+            emu.emu_decode16_i8_k4_rt(half, _p(w), _p(b))
+            assert (a == b).all()
+
+
 def test_strip_column_mapping_is_a_permutation(emu):
     cols = sorted(emu.emu_strip_col(q, lane) for q in range(4) for lane in range(32))
     assert cols == list(range(128))
