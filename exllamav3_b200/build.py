@@ -26,6 +26,10 @@ if os.environ.get("EXL3B_TC_DEBUG", "0") != "0":       # bring-up build: in-kern
     NVCC_FLAGS.append("-DEXL3B_TC_DEBUG")
 
 
+if os.environ.get("EXL3B_NVCC_EXTRA"):                   # experiment switches, e.g. EXL3B_NVCC_EXTRA="-DEXL3B_I8_K4_BRANCHFREE=1" (+ -f)
+    NVCC_FLAGS += os.environ["EXL3B_NVCC_EXTRA"].split()
+
+
 def _nvcc():
     nv = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nv) and shutil.which("nvcc") is None:
