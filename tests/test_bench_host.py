@@ -1,0 +1,85 @@
+"""
+bench.py's host logic without a GPU: the per-rank launch list of a token (what the reference's model code issues through the
+operator surface: q, k+v as one exl3_mgemm, o, gate+up as one exl3_mgemm, down per layer, then lm_head),
+the tensor-parallel shard shapes, the algorithmic byte count of the roofline, and the control flow of Token.run() for the
+NCCL and the fused row-parallel variants -- with a recording stand-in for the extension (no kernel runs here).
+"""
+import os, sys
+import pytest
+import torch
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+import bench
+
+TINY = dict(hidden=256, inter=512, q=256, kv=128, layers=2, vocab=640, K=4, head_K=6)
+
+
+class Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def exl3_gemm(self, A, B, C, suh, A_had, svh, fsi, mcg, mul1, fns):
+        assert A.shape[-1] == B.shape[0] * 16 and C.shape[-1] == B.shape[1] * 16 and mul1 and not mcg
+        self.calls.append(("gemm", A.shape[-1], C.shape[-1]))
+        return 210
+
+    def exl3_gemm_allreduce(self, A, B, C, suh, A_had, svh, mcg, mul1):
+        assert A_had is None and mul1 and not mcg
+        self.calls.append(("gemm_ar", A.shape[-1], C.shape[-1]))
+        return 211
+
+    def exl3_mgemm(self, A, B, C, suh, A_had, svh, indices, weights, K, fsi, mcg, mul1, mn, mx, fns):
+        assert indices is None and weights is None and B.numel() == 2 and C.shape[0] == 2 and mn == -1 and mx == -1
+        self.calls.append(("mgemm", A.shape[-1], C.shape[-1]))
+        return 210
+
+
+@pytest.mark.parametrize("tp", [1, 2, 4])
+def test_token_launch_list_and_run_control_flow(tp, monkeypatch):
+    dev = torch.device("cpu")
+    tok = bench.Token(TINY, tp, 0, dev)
+    sh = lambda x: max(128, (x // tp) // 128 * 128) if tp > 1 else x
+    assert len(tok.mats) == 7 * TINY["layers"] + 1
+    assert len(tok.launches) == 5 * TINY["layers"] + 1          # k+v and gate+up fused: 161 launches for the 32-layer model
+    per_layer = [("gemm", 256, sh(256)), ("mgemm", 256, sh(128)), ("gemm", sh(256), 256), ("mgemm", 256, sh(512)), ("gemm", sh(512), 256)]
+    head = ("gemm", 256, sh(640) if tp > 1 else 640)
+
+    # (1) kernels only (the single-GPU bench, or --tp-shapes): no collective
+    rec = Recorder(); tok.ext = rec; tok.skip_reduce = True
+    tok.run()
+    assert rec.calls == per_layer * TINY["layers"] + [head]
+
+    # (2) NCCL variant: one all_reduce after every row-parallel output (o, down) when tp > 1
+    import torch.distributed as dist
+    reduced = []
+    monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: reduced.append(tuple(t.shape)))
+    rec = Recorder(); tok.ext = rec; tok.skip_reduce = False
+    tok.run()
+    assert rec.calls == per_layer * TINY["layers"] + [head]
+    assert len(reduced) == (2 * TINY["layers"] if tp > 1 else 0) and all(s == (1, 256) for s in reduced)
+
+    # (3) fused variant: the row-parallel GEMMs become exl3_gemm_allreduce, nothing else changes, no NCCL call
+    if tp > 1:
+        reduced.clear()
+        rec = Recorder(); tok.ext = rec; tok.fused_reduce = True
+        tok.run()
+        fused_layer = [c if i not in (2, 4) else ("gemm_ar",) + c[1:] for i, c in enumerate(per_layer)]
+        assert rec.calls == fused_layer * TINY["layers"] + [head]
+        assert reduced == []
+
+
+def test_algorithmic_bytes_match_survey_8d():
+    # 4096 x 4096, K = 4, m = 1, fp16 out: 8,388,608 + 8,192 + 8,192 + 16,384 = 8,421,376 B
+    assert bench.alg_bytes(1, 4096, 4096, 4, False) == 8421376
+    cfg = bench.MODELS["llama-3.1-8b"]
+    layer, head = bench.token_plan(cfg, 1)
+    total = cfg["layers"] * sum(bench.alg_bytes(1, k, n, K, f) for (_, k, n, K, f, _) in layer) + bench.alg_bytes(1, *head[1:5])
+    assert abs(total / 1e9 - 3.884) < 0.02                       # "Llama-8B token: 3.884 GB"
+    assert bench.weights_per_token(cfg) == 32 * 218103808 + 4096 * 128256
+    # TP shards are multiples of 128 channels and never empty
+    for tp in (2, 4, 8):
+        for model in bench.MODELS.values():
+            layer, head = bench.token_plan(model, tp)
+            for (_, k, n, _, _, _) in layer + [head]:
+                assert k % 128 == 0 and n % 128 == 0 and k >= 128 and n >= 128
