@@ -14,7 +14,7 @@ There is no CPU or torch fallback: if the shared library is missing this module 
 raises RuntimeError when given a non-CUDA tensor.
 """
 from __future__ import annotations
-import ctypes, os
+import ctypes, os, weakref
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -212,6 +212,46 @@ def exl3_gemm_allreduce(A, B, C, suh, A_had, svh, mcg, mul1) -> int:
             size_m, size_k, size_n, K, _cb(mcg, mul1), int(c_fp32)))
 
 
+# Dense exl3_mgemm calls the int8 tensor-core kernel cannot take (other codebooks, or 5..32 rows: the reference's model code
+# fuses k+v and gate+up up to 32 rows, modules/attn.py:603, modules/mlp.py:726) run on the CUDA-core kernels by default.
+# EXL3B_MGEMM_SPLIT=1 instead issues one exact tcgen05 exl3_gemm per matrix (same results as separate calls): that needs the
+# pointer tables' VALUES on the host, so each table tensor is copied back once and remembered for as long as that tensor
+# object lives and is not modified (weak reference + version counter; never keyed on an address, which the caching allocator
+# reuses).  A table first seen during CUDA-graph capture cannot be copied: such a call keeps the default path.
+# Opt-in until it has run on hardware (round 2).
+_MGEMM_SPLIT = os.environ.get("EXL3B_MGEMM_SPLIT", "0") != "0"
+_table_cache: dict = {}
+
+
+def _host_table(t: torch.Tensor):
+    key = id(t)
+    ent = _table_cache.get(key)
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    if t.is_cuda and torch.cuda.is_current_stream_capturing():
+        return None
+    vals = [int(v) for v in t.detach().cpu().tolist()]
+    _table_cache[key] = (weakref.ref(t, lambda _r, key=key: _table_cache.pop(key, None)), t._version, vals)
+    return vals
+
+
+def _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, k, n, force_num_sms):
+    """One exl3b_gemm per matrix for a dense multi-matrix call; returns the path tag or None if the tables are unavailable."""
+    tb, ts, tv = _host_table(B), _host_table(suh), _host_table(svh)
+    if tb is None or ts is None or tv is None or len(tb) < bszm_out:
+        return None
+    a0, c0, h0 = A.data_ptr(), C.data_ptr(), A_had.data_ptr()
+    a_stride = 0 if bszm_in == 1 else m * k * 2
+    c_stride = m * n * (4 if c_fp32 else 2)
+    tag = 0
+    with torch.cuda.device(A.device):
+        stream = _stream(A)
+        for j in range(bszm_out):
+            tag = _check(_lib.exl3b_gemm(stream, a0 + j * a_stride, tb[j], c0 + j * c_stride, ts[j], h0 + j * m * k * 2, tv[j],
+                                         m, k, n, int(K), cb, int(c_fp32), -1, int(force_num_sms)))
+    return tag
+
+
 def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_idx: int, mcg, mul1,
                min_index: int, max_index: int, force_num_sms: int, num_tokens: int = 1,
                size_n_list=None, c_ptrs=None) -> int:
@@ -249,6 +289,12 @@ def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_i
         if weights.dim() != 2:
             raise RuntimeError("weights: incorrect number of dimensions, must be 2")
         _dtype(weights, torch.half, "weights")
+    cb = _cb(mcg, mul1)
+    if (_MGEMM_SPLIT and indices is None and weights is None and size_n_list is None and min_index < 0 and num_tokens == 1
+            and not (cb == 2 and m <= 4) and bszm_in in (1, bszm_out) and m >= 1 and bszm_out >= 1 and k % 128 == 0 and n % 128 == 0):
+        tag = _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, k, n, force_num_sms)
+        if tag is not None:
+            return tag
     with torch.cuda.device(A.device):
         return _check(_lib.exl3b_mgemm(
             _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had), _ptr(svh),

@@ -97,3 +97,56 @@ def test_linear_exl3_tp_slice_host_logic():
     assert torch.equal(row1.trellis, lin.trellis[8:16]) and torch.equal(row1.suh, lin.suh[128:256])
     assert row0.bias is not None and row1.bias is None            # bias only on the shard with first == 0
     assert col.trellis.is_contiguous() and row1.trellis.is_contiguous()
+
+
+def test_mgemm_split_host_logic(monkeypatch):
+    """EXL3B_MGEMM_SPLIT: a dense exl3_mgemm the int8 kernel cannot take becomes one exl3b_gemm per matrix with the right
+    pointers (tables read back once per tensor object, cache invalidated by modification).  Recording stand-in, no kernels."""
+    import contextlib
+    from exllamav3_b200 import ext
+    calls = []
+
+    class FakeLib:
+        def exl3b_gemm(self, stream, A, B, C, suh, A_had, svh, m, k, n, K, cb, c_fp32, fsi, fns):
+            calls.append(("gemm", A, B, C, suh, A_had, svh, m, k, n, K, cb, c_fp32)); return 200
+        def exl3b_mgemm(self, *a):
+            calls.append(("mgemm",)); return 100
+        def exl3b_last_error(self): return b""
+
+    monkeypatch.setattr(ext, "_lib", FakeLib())
+    monkeypatch.setattr(ext, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(ext, "_stream", lambda t: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(ext, "_MGEMM_SPLIT", True)
+    m, k, n, K = 8, 256, 384, 4
+    A = torch.zeros((1, m, k), dtype=torch.half); C = torch.zeros((2, m, n), dtype=torch.float)
+    Ah = torch.zeros((2, m, k), dtype=torch.half)
+    B = torch.tensor([1000, 2000]); su = torch.tensor([3000, 4000]); sv = torch.tensor([5000, 6000])
+    tag = ext.exl3_mgemm(A, B, C, su, Ah, sv, None, None, K, -1, False, True, -1, -1, 0)      # mul1 but 8 rows -> split
+    assert tag == 200 and [c[0] for c in calls] == ["gemm", "gemm"]
+    g0, g1 = calls
+    assert g0[1] == g1[1] == A.data_ptr()                                   # shared input
+    assert (g0[2], g0[4], g0[6]) == (1000, 3000, 5000) and (g1[2], g1[4], g1[6]) == (2000, 4000, 6000)
+    assert g1[3] - g0[3] == m * n * 4 and g1[5] - g0[5] == m * k * 2        # C[j], A_had[j]
+    assert g0[7:] == (m, k, n, K, 2, 1)
+    # table modified in place -> re-read
+    calls.clear(); B[1] = 2222
+    ext.exl3_mgemm(A, B, C, su, Ah, sv, None, None, K, -1, False, True, -1, -1, 0)
+    assert calls[1][2] == 2222
+    # per-matrix inputs; 3INST codebook at one row also splits (the int8 kernel is mul1 only)
+    calls.clear()
+    A2 = torch.zeros((2, 1, k), dtype=torch.half); C2 = torch.zeros((2, 1, n), dtype=torch.half)
+    ext.exl3_mgemm(A2, B, C2, su, Ah, sv, None, None, K, -1, False, False, -1, -1, 0)
+    assert [c[0] for c in calls] == ["gemm", "gemm"] and calls[1][1] - calls[0][1] == k * 2 and calls[0][11] == 0 and calls[0][12] == 0
+    # what stays on exl3b_mgemm: int8-eligible calls, routed calls, and everything when the switch is off
+    calls.clear()
+    ext.exl3_mgemm(A[:, :4], B, C[:, :4], su, Ah, sv, None, None, K, -1, False, True, -1, -1, 0)
+    idx = torch.zeros((1, 2), dtype=torch.long)
+    ext.exl3_mgemm(A, B, C, su, Ah, sv, idx, None, K, -1, False, True, -1, -1, 0)
+    monkeypatch.setattr(ext, "_MGEMM_SPLIT", False)
+    ext.exl3_mgemm(A, B, C, su, Ah, sv, None, None, K, -1, False, True, -1, -1, 0)
+    assert [c[0] for c in calls] == ["mgemm", "mgemm", "mgemm"]
+    # the cache does not outlive the tensor
+    n_before = len(ext._table_cache); del B, su, sv
+    import gc; gc.collect()
+    assert len(ext._table_cache) <= n_before - 3

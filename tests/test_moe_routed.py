@@ -142,3 +142,33 @@ def test_routed_i8_mgemm_mixtral_shapes_properties(cuda):
             assert float((outs[1 + j] - y).abs().max() / y.abs().max()) < 1e-5
     finally:
         ext.set_gemm_path(prev)
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("m,cb", [(8, 2), (32, 2), (1, 0), (17, 1)])
+def test_mgemm_split_matches_fused_default(cuda, monkeypatch, m, cb):
+    """EXL3B_MGEMM_SPLIT (ext.py): dense multi-matrix calls the int8 kernel cannot take, issued as one exact tcgen05 exl3_gemm
+    per matrix, against the default (CUDA-core multi-matrix kernels) and the fp64 oracle."""
+    from exllamav3_b200 import ext
+    k, n, K, nm = 512, 384, 4, 2
+    mats = [orc.make_synthetic(k, n, K, seed=300 + 7 * e, m=m) for e in range(nm)]
+    trs = [T(t[0], cuda) for t in mats]; suhs = [T(t[1], cuda) for t in mats]; svhs = [T(t[2], cuda) for t in mats]
+    ptr = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.long, device=cuda)
+    pt, ps, pv = ptr(trs), ptr(suhs), ptr(svhs)
+    x = np.random.default_rng(m).standard_normal((1, m, k)).astype(np.float16)
+    Ah = torch.empty((nm, m, k), dtype=torch.half, device=cuda)
+    outs = {}
+    for split in (False, True):
+        monkeypatch.setattr(ext, "_MGEMM_SPLIT", split)
+        C = torch.full((nm, m, n), float("nan"), dtype=torch.float, device=cuda)
+        before = ext.launch_count()
+        tag = ext.exl3_mgemm(T(x, cuda), pt, C, ps, Ah, pv, None, None, K, -1, cb == 1, cb == 2, -1, -1, 0)
+        torch.cuda.synchronize()
+        assert tag == (ext.EXL3B_TAG_TC if split else ext.EXL3B_TAG_SIMT)
+        outs[split] = C.cpu().numpy()
+    for j in range(nm):
+        ref = orc.exl3_gemm_f64(x[0], mats[j][0], mats[j][1], mats[j][2], K, cb)
+        for split in (False, True):
+            mx, rms = rel_err(outs[split][j], ref)
+            assert mx <= 2e-3 and rms <= 1e-3, (split, j, mx, rms)
