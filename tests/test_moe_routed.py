@@ -172,3 +172,30 @@ def test_mgemm_split_matches_fused_default(cuda, monkeypatch, m, cb):
         for split in (False, True):
             mx, rms = rel_err(outs[split][j], ref)
             assert mx <= 2e-3 and rms <= 1e-3, (split, j, mx, rms)
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("m", [5, 8])
+def test_dense_mgemm_i8_eight_row_variant(cuda, m):
+    """The 8-row instantiation of the int8 kernel (verified for single matrices, test_gpu_parity.py::test_gemm_i8_tensor_core_path)
+    in its multi-matrix mode (verified for <= 4 rows): the combination is what a batch-5..8 decode step's fused k+v / gate+up
+    would use if exl3b_mgemm auto-selected tag 210 up to 8 rows instead of falling back to the CUDA-core kernels."""
+    from exllamav3_b200 import ext
+    k, n, K, nm = 1024, 384, 4, 2
+    mats, keep, (pt, ps, pv) = _setup(cuda, nm, k, n, K, m, seed=40 + m)
+    x = np.random.default_rng(m).standard_normal((1, m, k)).astype(np.float16)
+    Ah = torch.empty((nm, m, k), dtype=torch.half, device=cuda)
+    prev = ext.set_gemm_path(ext.EXL3B_TAG_TC_I8)
+    try:
+        C = torch.full((nm, m, n), float("nan"), dtype=torch.float, device=cuda)
+        before = ext.launch_count()
+        tag = ext.exl3_mgemm(T(x, cuda), pt, C, ps, Ah, pv, None, None, K, -1, False, True, -1, -1, 0)
+        torch.cuda.synchronize()
+        assert tag == ext.EXL3B_TAG_TC_I8 and ext.launch_count() - before == 1
+        for j in range(nm):
+            ref = orc.exl3_gemm_f64(x[0], mats[j][0], mats[j][1], mats[j][2], K, 2)
+            mx, rms = rel_err(C[j].cpu().numpy(), ref)
+            assert mx <= 2e-3 and rms <= 1e-3, (j, mx, rms)
+    finally:
+        ext.set_gemm_path(prev)
