@@ -238,6 +238,85 @@ class Token:
                                False, True, -1, -1, 0)
 
 
+def qgemm_section(tok, cfg, stream, hbm_peak):
+    """
+    The second half of BASELINE.json's metric, measured live on rank 0 at N = 1 AFTER the timed token (never inside it):
+      decode_hbm      per matrix shape of the model, the batch-1 qgemm's achieved HBM GB/s = algorithmic bytes /
+                      launch time, from one CUDA-graph replay of that shape's 32 layer instances back to back (distinct weight
+                      buffers, 67-940 MB per shape; weights are loaded evict-first), CUDA events on the launching stream
+      prefill_tensor  the prefill sibling of the same linear (reconstruct_had + tcgen05 dense GEMM, LinearEXL3.forward for
+                      rows > 144) at batch 32 x 2048 rows: achieved TFLOP/s (2 m k n) against the measured dense bf16 peaks
+    """
+    import torch
+    from exllamav3_b200 import ext, LinearEXL3
+    out = {"decode_hbm": {}, "prefill_tensor": {}}
+    by_name = {}
+    for mt in tok.mats:
+        by_name.setdefault(mt["name"], []).append(mt)
+    for name, mats in by_name.items():
+        def run():
+            for mt in mats:
+                ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, False, True, 0)
+        with torch.cuda.stream(stream):
+            run()
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            run()
+        reps = 3 if len(mats) > 1 else 6
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(reps):
+                    g.replay()
+                e1.record(stream)
+            e1.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (reps * len(mats))
+            best = us if best is None else min(best, us)
+        mt = mats[0]
+        b = alg_bytes(1, mt["k"], mt["n"], mt["K"], mt["c_fp32"])
+        out["decode_hbm"][name] = {"k": mt["k"], "n": mt["n"], "K": mt["K"], "us_per_launch": round(best, 2),
+                                   "GBps": round(b / best / 1e3, 1), "frac_of_hbm_peak": round(b / best / 1e3 / hbm_peak, 3),
+                                   "distinct_weight_MB": round(len(mats) * mt["k"] * mt["n"] * mt["K"] / 8 / 1e6)}
+        del g
+    # prefill: batch 32 x seq 2048 rows through the reference-facing linear (rows > 144 -> reconstruct + dense GEMM)
+    peaks = {}
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"burst": float(d["bf16_tflops"]), "sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))}
+    except Exception:
+        peaks = {"burst": 2250.0, "sustained": 2250.0}          # nominal dense bf16 (B200_PROFILING.md fallback)
+    dev = tok.dev
+    gen = torch.Generator(device=dev); gen.manual_seed(7)
+    h = cfg["hidden"]
+    for (k, n, m) in ((h, cfg["q"], 32 * 2048), (h, cfg["inter"], 8 * 2048)):
+        mt = next(t for t in tok.mats if t["k"] == k and t["n"] == n)
+        lin = LinearEXL3(None, k, n, suh=mt["suh"], svh=mt["svh"], trellis=mt["tr"], mul1=torch.zeros((), dtype=torch.int, device=dev))
+        x = torch.randn((m, k), generator=gen, device=dev).half()
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                y = lin.forward(x, {})
+        stream.synchronize()
+        it = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(it):
+                y = lin.forward(x, {})
+            e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / it
+        tf = 2.0 * m * k * n / ms / 1e9
+        out["prefill_tensor"][f"{k}x{n}_m{m}"] = {"rows": m, "ms": round(ms, 3), "tflops": round(tf, 1),
+                                                   "frac_of_measured_bf16_burst": round(tf / peaks["burst"], 3),
+                                                   "frac_of_measured_bf16_sustained": round(tf / peaks["sustained"], 3),
+                                                   "path": "reconstruct_had + tcgen05 dense GEMM (includes the weight reconstruction every call)"}
+        del x, y, lin
+    return out
+
+
 def run_gpu_arm(args, cfg):
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -365,6 +444,17 @@ def run_gpu_arm(args, cfg):
         check = {"matrix": name, "max_rel_err_vs_cpu_path": err}
         assert err < 1e-2, f"GPU result deviates from the CPU path: {err}"
 
+    qgemm = None
+    if rank == 0 and world == 1 and not args.tp_shapes and not args.no_qgemm:
+        try:
+            qgemm = qgemm_section(tok, cfg, stream, peak)
+        except Exception as e:                   # never lose the bench line over the supplementary section
+            qgemm = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+
     if rank == 0:
         line = {
             "metric": "decode tok/s Llama-3.1-8B 4.0bpw b=1 (qgemm path)", "value": 1000.0 / ms_per_step, "unit": "tok/s",
@@ -391,6 +481,7 @@ def run_gpu_arm(args, cfg):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "check": check,
+            "qgemm": qgemm,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -413,6 +504,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-qgemm", action="store_true", help="skip the per-shape qgemm GB/s + prefill tensor-pipe section (N = 1 only)")
     ap.add_argument("--fused-allreduce", action="store_true",
                     help="N > 1: row-parallel outputs through exl3_gemm_allreduce (one kernel) instead of exl3_gemm + NCCL; "
                          "opt-in until verified on hardware")

@@ -83,3 +83,43 @@ def test_algorithmic_bytes_match_survey_8d():
             layer, head = bench.token_plan(model, tp)
             for (_, k, n, _, _, _) in layer + [head]:
                 assert k % 128 == 0 and n % 128 == 0 and k >= 128 and n >= 128
+
+
+def test_qgemm_section_control_flow(monkeypatch):
+    """bench.py's supplementary section (per-shape decode GB/s, prefill TFLOP/s) with every CUDA facility stubbed: checks the
+    Python control flow, the shapes it times and the keys it reports -- so that a typo cannot cost the round's bench line."""
+    import contextlib
+    import exllamav3_b200
+    from exllamav3_b200 import ext, LinearEXL3
+
+    class Ev:
+        def __init__(self, enable_timing=True): pass
+        def record(self, s=None): pass
+        def synchronize(self): pass
+        def elapsed_time(self, other): return 1.0           # ms
+
+    class Graph:
+        def replay(self): pass
+
+    class Stream:
+        def synchronize(self): pass
+
+    calls = []
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, stream=None: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(ext, "exl3_gemm", lambda *a: calls.append(("gemm", a[0].shape[-1], a[2].shape[-1])) or 210)
+    monkeypatch.setattr(LinearEXL3, "forward", lambda self, x, params, out_dtype=None: calls.append(("prefill", tuple(x.shape), self.out_features)) or x)
+    tok = bench.Token(TINY, 1, 0, torch.device("cpu"))
+    out = bench.qgemm_section(tok, TINY, Stream(), 6576.1)
+    assert set(out["decode_hbm"]) == {"q", "k", "v", "o", "gate", "up", "down", "lm_head"}
+    q = out["decode_hbm"]["q"]
+    assert (q["k"], q["n"], q["K"]) == (256, 256, 4) and q["us_per_launch"] > 0 and q["GBps"] > 0 and q["frac_of_hbm_peak"] >= 0
+    # every shape: one warm-up pass + one captured pass over its layer instances
+    assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"]           # q and o share the shape
+    assert calls.count(("gemm", 256, 640)) == 2
+    pre = [c for c in calls if c[0] == "prefill"]
+    assert {(c[1], c[2]) for c in pre} == {((65536, 256), 256), ((16384, 256), 512)} and len(pre) == 2 * 7
+    for v in out["prefill_tensor"].values():
+        assert v["tflops"] > 0 and v["frac_of_measured_bf16_burst"] > 0 and v["rows"] in (65536, 16384)
