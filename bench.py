@@ -13,6 +13,9 @@ between steps).  Attention / norm / rope are not part of the hot path (SURVEY.md
              against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline   the oracle port of the reference's torch dequant+matmul path (LinearEXL3.get_weight_tensor semantics)
              timed on the host cores on a bounded sample (rank 0, N=1)
+  qgemm      (N=1) the other half of BASELINE.json's metric, measured after the timed token: per matrix shape the batch-1
+             qgemm's HBM GB/s and fraction of the measured copy peak, and the batch-32 prefill sibling's TFLOP/s against the
+             measured dense bf16 peaks (supplementary: a failure there is reported in the key, never loses the line)
 
 N > 1 (torchrun): the same token, tensor-parallel: q/k/v/gate/up column-sharded, o/down row-sharded with one
 all-reduce (sum) per row-parallel output, lm_head column-sharded ("scaling": "strong").
