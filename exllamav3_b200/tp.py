@@ -115,3 +115,20 @@ def row_parallel_forward(shard, x_local: torch.Tensor, params: dict, out_dtype=N
 def column_parallel_forward(shard, x: torch.Tensor, params: dict, out_dtype=None) -> torch.Tensor:
     """No communication: every rank keeps its slice of the output channels."""
     return shard.forward(x, params, out_dtype)
+
+
+def gather_columns(y_local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """
+    Full-width output of a column-parallel linear on every rank (the lm_head case, SURVEY.md 8e: col-split + gather).
+    Shards may differ in width (split_ranges gives earlier ranks the remainder), so the gather is padded to the widest.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return y_local
+    world = dist.get_world_size(group)
+    ranges = split_ranges(total, world)
+    widest = max(b - a for a, b in ranges)
+    pad = torch.zeros(tuple(y_local.shape[:-1]) + (widest,), dtype=y_local.dtype, device=y_local.device)
+    pad[..., :y_local.shape[-1]] = y_local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[..., :b - a] for p, (a, b) in zip(parts, ranges)], dim=-1)

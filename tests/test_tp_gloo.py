@@ -34,9 +34,7 @@ def _worker(rank, world, port, ret):
         # column parallel: no communication, gather only to verify
         cs = tp.column_shard(lin, rank, world)
         yc = local_gemm(cs, x)
-        parts = [torch.empty_like(yc) for _ in range(world)]
-        dist.all_gather(parts, yc)
-        err_c = float((torch.cat(parts, dim=1) - torch.from_numpy(full)).abs().max())
+        err_c = float((tp.gather_columns(yc, n) - torch.from_numpy(full)).abs().max())
 
         # row parallel: partial with full epilogue on every rank, one all-reduce
         rs = tp.row_shard(lin, rank, world)
@@ -86,7 +84,12 @@ def _worker_rank_ordered(rank, world, port, ret):
         ref = torch.from_numpy(orc.exl3_gemm_f64(x, tr, suh, svh, K, cb))
         everyone = [torch.empty_like(acc) for _ in range(world)]
         dist.all_gather(everyone, acc)
-        ret[rank] = (float((acc.double() - ref).abs().max() / ref.abs().max()), all(torch.equal(everyone[0], e) for e in everyone))
+        # column-parallel with UNEVEN shards (4 units of 128 over 3 ranks: 256 + 128 + 128) gathered to full width
+        cs = tp.column_shard(lin, rank, world)
+        yc = torch.from_numpy(orc.exl3_gemm_f64(x, cs.trellis.numpy(), cs.suh.numpy(), cs.svh.numpy(), cs.K, cb))
+        err_cols = float((tp.gather_columns(yc, n) - ref).abs().max())
+        ret[rank] = (float((acc.double() - ref).abs().max() / ref.abs().max()),
+                     all(torch.equal(everyone[0], e) for e in everyone) and err_cols < 1e-9 and cs.out_features == (256 if rank == 0 else 128))
     finally:
         dist.destroy_process_group()
 
