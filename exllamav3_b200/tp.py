@@ -77,7 +77,8 @@ def enable_fused_allreduce(max_elems: int = 4 * 16384, group=None) -> None:
 def disable_fused_allreduce(group=None) -> None:
     from . import ext
     if _fused["on"]:
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         if dist.is_initialized():
             dist.barrier(group)             # nobody unmaps while a peer may still write
         ext.tp_free()

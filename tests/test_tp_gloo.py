@@ -105,6 +105,36 @@ def test_tp_rank_ordered_sum_is_identical_on_all_ranks_world3():
         assert err < 2e-3 and identical
 
 
+def _worker_fused_setup(rank, world, port, ret):
+    """tp.enable_fused_allreduce's collective plumbing with the CUDA IPC calls stubbed: every rank must hand tp_attach the
+    world handles concatenated in RANK order, and nobody may proceed before everybody has attached (barrier)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from exllamav3_b200 import ext, tp
+        seen = {}
+        ext.tp_alloc = lambda r, w, me: seen.update(alloc=(r, w, me)) or bytes([0x40 + r]) * ext.TP_HANDLE_BYTES
+        ext.tp_attach = lambda handles, w: seen.update(attach=(bytes(handles), w))
+        ext.tp_free = lambda: seen.update(freed=True)
+        tp.enable_fused_allreduce(max_elems=2048)
+        want = b"".join(bytes([0x40 + j]) * ext.TP_HANDLE_BYTES for j in range(world))
+        ok = seen["alloc"] == (rank, world, 2048) and seen["attach"] == (want, world) and tp._fused == {"on": True, "world": world, "max_elems": 2048}
+        tp.disable_fused_allreduce()
+        ok = ok and seen.get("freed") and tp._fused["on"] is False
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_allreduce_setup_plumbing_world3():
+    world, port = 3, 30317 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_fused_setup, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world and all(ret[r] for r in range(world))
+
+
 def test_split_ranges():
     from exllamav3_b200 import tp
     assert tp.split_ranges(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
