@@ -320,6 +320,30 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
     return out
 
 
+NCU_CAPTURE = os.path.join("profiles", "r01_ncu_i8_gate_4096x14336_K4_m1.csv")     # metric,unit,value rows of one --set full capture
+
+
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture, in bytes (units as ncu printed them)."""
+    import csv
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cap = {r[0]: (r[1], r[2]) for r in csv.reader(open(path)) if len(r) == 3}
+    total = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        unit, val = cap[key]
+        total += float(val) * mult[unit]
+    return total
+
+
+def ncu_traffic_per_launch(tok):
+    """DRAM traffic of the dominant kernel from the committed ncu capture (profiles/): measured bytes / algorithmic bytes of
+    the captured launch (gate shape), applied to the average launch of this step; None if the capture is missing."""
+    try:
+        return ncu_dram_bytes(os.path.join(ROOT, NCU_CAPTURE)) / alg_bytes(1, 4096, 14336, 4, True) * tok.alg_bytes / len(tok.launches)
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args, cfg):
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -421,14 +445,7 @@ def run_gpu_arm(args, cfg):
     achieved = tok.alg_bytes / (ms_per_step * 1e-3) / 1e9          # per rank (each rank streams its own shard)
     # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/): measured bytes / algorithmic bytes
     # of the captured launch, applied to the average launch of this step
-    traffic = None
-    try:
-        import csv
-        cap = {r[0]: r[2] for r in csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_i8_gate_4096x14336_K4_m1.csv"))) if len(r) == 3}
-        rd = float(cap["dram__bytes_read.sum"]) * 1e6 + float(cap["dram__bytes_write.sum"])
-        traffic = rd / alg_bytes(1, 4096, 14336, 4, True) * tok.alg_bytes / len(tok.launches)
-    except Exception:
-        pass
+    traffic = ncu_traffic_per_launch(tok)
     cpu_baseline = None
     check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
