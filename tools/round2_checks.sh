@@ -15,6 +15,10 @@ if [ "${1:-}" = "tp" ]; then
             bench.py --gpus 2 --steps 20 --warmup 3 $fl > "$out/bench_n2${fl:+_fused}.json" 2> "$out/bench_n2${fl:+_fused}.err"
         echo "bench n2 $fl rc=$?" | tee -a "$out/summary.txt"
     done
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29655 \
+        tools/tp_rowparallel_bench.py > "$out/tp_rowparallel.jsonl" 2> "$out/tp_rowparallel.err"
+    echo "row-parallel NCCL vs fused rc=$?" | tee -a "$out/summary.txt"
+    cat "$out/tp_rowparallel.jsonl"
     exit 0
 fi
 timeout 900 python -m pytest tests -q -m gpu -x > "$out/gpu_suite.log" 2>&1;  echo "gpu suite rc=$?" | tee "$out/summary.txt"
