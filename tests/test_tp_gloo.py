@@ -135,6 +135,48 @@ def test_fused_allreduce_setup_plumbing_world3():
     assert len(ret) == world and all(ret[r] for r in range(world))
 
 
+def _worker_expert_parallel(rank, world, port, ret):
+    """Expert-parallel MoE down-projection (BASELINE config 5; the reference partitions experts by contiguous index range and
+    all-reduces the outputs, modules/block_sparse_mlp.py:1679-1705, no all-to-all): every rank runs exl3_mgemm semantics with
+    the expert-range filter [lo, hi) and its LOCAL pointer tables, the weighted partial sums add up to the unsharded result."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import exl3_oracle as orc
+        E, k, n, K, m, topk = 4, 256, 128, 4, 1, 3
+        mats = [orc.make_synthetic(k, n, K, seed=60 + e, m=m) for e in range(E)]
+        trs = [t[0] for t in mats]; suhs = [t[1] for t in mats]; svhs = [t[2] for t in mats]
+        rng = np.random.default_rng(3)
+        xs = rng.standard_normal((topk, m, k)).astype(np.float16)
+        sel = [3, 0, 2]; wts = rng.uniform(0.1, 1.0, topk).astype(np.float16)
+        full = orc.exl3_mgemm(xs, trs, suhs, svhs, K, 2, np.float32, indices=sel, weights=wts, bszm_out=topk)[0]
+        per = E // world
+        lo, hi = rank * per, (rank + 1) * per
+        # compaction keeps the slot ORDER but slot j of the shard reads input A[j] (exl3_gemm_kernel.cuh:139-146): the caller
+        # passes the inputs of the retained slots, as the reference's expert-parallel path does
+        keep = [j for j, q in enumerate(sel) if lo <= q < hi]
+        xs_local = np.ascontiguousarray(np.concatenate([xs[keep], np.zeros((topk - len(keep), m, k), dtype=np.float16)], axis=0))
+        part = orc.exl3_mgemm(xs_local, trs[lo:hi], suhs[lo:hi], svhs[lo:hi], K, 2, np.float32, indices=sel, weights=wts,
+                              min_index=lo, max_index=hi, bszm_out=topk)[0]
+        t = torch.from_numpy(np.ascontiguousarray(part)).float()
+        dist.all_reduce(t)
+        ret[rank] = (float(np.abs(t.numpy() - full).max() / np.abs(full).max()), len(keep))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_expert_parallel_partials_sum_to_the_unsharded_result_world2():
+    world, port = 2, 30717 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_expert_parallel, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    assert sorted(ret[r][1] for r in range(world)) == [1, 2]          # experts {0} on rank 0, {3, 2} on rank 1
+    for r in range(world):
+        assert ret[r][0] < 1e-5, ret[r]
+
+
 def test_split_ranges():
     from exllamav3_b200 import tp
     assert tp.split_ranges(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
