@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexl3b200.so")
 
 SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "gemm_tc_i8_ar.cu", "gemm_tc_i8_routed.cu", "hgemm.cu", "hgemm_tc.cu"]
-HEADERS = ["common.cuh", "decode.cuh", "epilogue.cuh", "ptx.cuh", "tc_common.cuh", "gemm_tc_i8_body.cuh", os.path.join("..", "..", "include", "exl3b200.h")]
+HEADERS = ["common.cuh", "decode.cuh", "epilogue.cuh", "ptx.cuh", "tc_common.cuh", "gemm_tc_i8_body.cuh", "i8_math.cuh", os.path.join("..", "..", "include", "exl3b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

@@ -33,6 +33,7 @@
 // Measured history and the experiments that were not kept: profiles/r01_ncu_notes.md.
 #pragma once
 #include "tc_common.cuh"
+#include "i8_math.cuh"
 
 namespace exl3b {
 
@@ -60,7 +61,6 @@ __host__ __device__ constexpr int i8_b_bytes(int MR) { return MR <= 4 ? 4096 : 8
 __host__ __device__ constexpr int i8_b_stage(int MR) { return i8_b_bytes(MR) + 64; }
 constexpr int I8_SUB_UNITS = 96;                               // int32 accumulator safety: <= 12288 k per accumulation
 constexpr uint32_t I8_SENTINEL = 0xffffffffu;                  // "no partial sum here yet" in the split-K exchange buffer
-constexpr int I8_QMAX = 32512;                                 // |q| <= 127 * 256 + 0  -> hi in [-127, 127]
 
 // optional shared-memory cache of the whole transformed activation (m x k fp16) and of the per-block digit sums, filled by
 // the CTA prologue: the per-unit transform then is an 8-byte LDS + quantise instead of a global load + Hadamard
@@ -426,12 +426,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                     #pragma unroll
                     for (int e = 0; e < 4; ++e)
                     {
-                        const int q = __float2int_rn(v[e] * inv_scale[r]);
-                        const int hi = (q + 128) >> 8;
-                        const int lo = q - (hi << 8);
-                        qs += q;
-                        hi_w[e] = (uint32_t) (hi & 0xff) * 0x01010101u;          // digit replicated over the 4 product bytes
-                        lo_w[e] = (uint32_t) (lo & 0xff) * 0x01010101u;
+                        i8_digits(v[e], inv_scale[r], qs, hi_w[e], lo_w[e]);     // digits replicated over the 4 product bytes
                     }
                     // chunk = lane (4 k-values x 4 bytes = 16 B), N-rows 2r (hi) and 2r+1 (lo): row group r / 4, local rows 2 (r % 4), +1
                     uint8_t* drow = dst + (r >> 2) * 4096 + (lane * 8 + 2 * (r & 3)) * 16;
@@ -699,10 +694,10 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                     {
                         const int T = s_tout[dbuf * MR + r];
                         // sum_k q_k (bytesum_kn - 510), exact in 64-bit
-                        const long long sp = 256ll * (int) rr[2 * r] + (long long) (int) rr[2 * r + 1] - 510ll * T;
+                        const long long sp = i8_centred_sum((int) rr[2 * r], (int) rr[2 * r + 1], T);
                         const float mx = __uint_as_float(s_absmax[r]);
                         const float scale = mx / (float) I8_QMAX;
-                        facc[r] += scale * (k_inv * (float) sp + c1 * (float) T);
+                        facc[r] += i8_assemble(sp, T, scale, k_inv, c1);
                     }
                 }
                 tc_fence_before();

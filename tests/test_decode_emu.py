@@ -123,3 +123,34 @@ def test_emulation_builds_from_the_library_header():
     src = open(SRC).read()
     assert '#include "../../exllamav3_b200/csrc/decode.cuh"' in src
     assert "EXL3B_HOST_EMU" in open(HDR).read()
+
+
+@pytest.mark.parametrize("K", [2, 4, 6])
+def test_i8_path_arithmetic_from_device_headers_matches_oracle_model(emu, K):
+    """
+    The int8 tensor-core path's arithmetic, run on the host FROM THE DEVICE HEADERS (csrc/i8_math.cuh digits + reassembly,
+    csrc/decode.cuh product words, byte sums standing in for tcgen05.mma.kind::i8), against the oracle's independent fp64
+    model of the path (oracle.exl3_gemm_i8_model): same result to fp32 round-off.  Also asserts what the kernel relies on:
+    digits replicated over four bytes, hi in [-127, 127], s32 accumulators never overflow at these sizes.
+    """
+    emu.emu_i8_row.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int,
+                               ctypes.POINTER(ctypes.c_float)]
+    k, n = 512, 256
+    tr, suh, svh, x = orc.make_synthetic(k, n, K, seed=11 * K, m=3)
+    xh = orc.had_r_128(x, pre_scale=suh).astype(np.float32)                  # bit-exact fp16 transformed activations
+    tiles = np.ascontiguousarray(tr).view(np.uint16).reshape(k // 16, n // 16, 16 * K).copy().view(np.uint32)
+    want = orc.exl3_gemm_i8_model(x, tr, suh, svh, K)                        # (m, n) fp64, after output Hadamard and svh
+    H = orc.hadamard_matrix_128() * float(np.float32(0.088388347648))
+    for r in range(x.shape[0]):
+        acc = np.zeros(n, dtype=np.float32)
+        row = np.ascontiguousarray(xh[r])
+        rc = emu.emu_i8_row(K, tiles.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), row.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                            k, n, acc.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert rc == 0, rc
+        y = (acc.astype(np.float64).reshape(n // 128, 128) @ H).reshape(n) * svh.astype(np.float64)
+        err = np.abs(y - want[r]).max() / np.abs(want[r]).max()
+        assert err < 2e-6, (K, r, err)
+    # an all-zero row quantises to zero digits and a zero output
+    z = np.zeros(k, dtype=np.float32); acc = np.ones(n, dtype=np.float32)
+    assert emu.emu_i8_row(K, tiles.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), z.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), k, n,
+                          acc.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == 0 and (acc == 0).all()
