@@ -116,6 +116,10 @@ class LinearEXL3:
 
     def forward(self, x: torch.Tensor, params: dict, out_dtype: torch.dtype | None = None) -> torch.Tensor:
         # modules/quant/exl3.py:114-139
+        if "ovr" in params:                      # per-call module override table (exl3.py:121-124)
+            ovr = params["ovr"]
+            if self.key in ovr and getattr(ovr[self.key], "inner", None) is not self:
+                return ovr[self.key].forward(x, params, out_dtype)
         assert x.is_contiguous(), f"LinearEXL3 {self.key}: non-contiguous input {tuple(x.shape)}"
         reconstruct = params.get("reconstruct")
         if not reconstruct:
