@@ -158,3 +158,39 @@ def test_every_reference_call_site_of_the_qgemm_surface_fits_the_shim():
     # the call sites SURVEY.md 8b names exist and were checked
     assert seen["exl3_mgemm"] >= 8 and seen["hgemm"] >= 3 and seen["had_r_128"] >= 2 and seen["reconstruct"] >= 2
     assert seen["reconstruct_had_slice"] >= 2 and seen["reconstruct_slice"] >= 1 and seen["exl3_gemv_int8_max_k"] >= 1
+
+
+def test_reference_use_mgemm_policy_with_the_shims_answer(monkeypatch):
+    """model/config.py:48-64, the reference's OWN policy function, evaluated with this shim's exl3_gemv_int8_max_k (0): k+v and
+    gate+up stay fused for every bitrate -- the launch list bench.py times (161 launches) -- whereas with the reference
+    extension's answer on Blackwell (6) the wide 4-bpw gate+up pair is unfused (225-launch variant, bench.py --no-fuse)."""
+    from exllamav3_b200 import ext
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        monkeypatch.setitem(sys.modules, name, m)
+
+    mod("exllamav3"); mod("exllamav3.model"); mod("exllamav3.util")
+    mod("exllamav3.util.rope", RopeSettings=object, RopeStyle=object)
+    mod("exllamav3.loader", SafetensorsCollection=object)
+    mod("exllamav3.util.file", read_dict=None, no_value=None, no_default=None)
+    mod("exllamav3.ext", exllamav3_ext=ext)
+    for v in ("EXL3_INT8_GEMV", "EXL3_MGEMM_K_THRESHOLD", "EXL3_MGEMM_N_THRESHOLD"):
+        monkeypatch.delenv(v, raising=False)
+    spec = importlib.util.spec_from_file_location("exllamav3.model.config", os.path.join(REF, "model", "config.py"))
+    cfg = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "exllamav3.model.config", cfg)
+    spec.loader.exec_module(cfg)
+    ip = cfg.InferParams()
+    monkeypatch.setattr(ext, "_check", lambda rc: 148)                      # no device here: the index check is not under test
+    assert ext.exl3_gemv_int8_max_k(0) == 0
+    for K in range(1, 9):
+        assert ip.use_mgemm(K, 14336, mul1=True, device="cuda:0")          # gate/up: fused at every bitrate
+        assert ip.use_mgemm(K, 1024, mul1=True, device="cuda:0")           # k/v
+        assert ip.use_mgemm(K, 14336, mul1=False, device="cuda:0")         # other codebooks are always fused
+    monkeypatch.setattr(ext, "exl3_gemv_int8_max_k", lambda dev: 6)        # what the reference's own extension reports on sm_100
+    assert not ip.use_mgemm(4, 14336, mul1=True, device="cuda:0")          # wide 4 bpw pair: unfused there
+    assert ip.use_mgemm(4, 1024, mul1=True, device="cuda:0")               # narrow outputs stay fused either way
+    assert ip.use_mgemm(7, 14336, mul1=True, device="cuda:0")
