@@ -194,3 +194,38 @@ def test_reference_use_mgemm_policy_with_the_shims_answer(monkeypatch):
     assert not ip.use_mgemm(4, 14336, mul1=True, device="cuda:0")          # wide 4 bpw pair: unfused there
     assert ip.use_mgemm(4, 1024, mul1=True, device="cuda:0")               # narrow outputs stay fused either way
     assert ip.use_mgemm(7, 14336, mul1=True, device="cuda:0")
+
+
+def test_reference_tp_import_split_equals_tp_slice(ref_exl3):
+    """The reference's OWN shard construction (LinearEXL3.tp_export / tp_import_split, modules/quant/exl3.py:268-330), run with a
+    trivial in-process stand-in for its SHM producer / consumer transport, against this repo's LinearEXL3.tp_slice."""
+    ref_mod, _ = ref_exl3
+    from exllamav3_b200 import LinearEXL3 as Mirror, tp
+
+    class Producer:
+        def send(self, t): return t
+
+    class Consumer:
+        def recv(self, t, cuda=False, slice_dim=None, first=None, last=None):
+            if t is None:
+                return None
+            return t if slice_dim is None else t.narrow(slice_dim, first, last - first).contiguous()
+
+    k, n = 512, 768
+    tens = _tensors(k, n)
+    g = torch.Generator().manual_seed(5)
+    tens["suh"] = torch.randn(k, generator=g).half(); tens["svh"] = torch.randn(n, generator=g).half()
+    bias = torch.randn(n, generator=g).half()
+    ref_full = ref_mod.LinearEXL3(None, k, n, bias=bias, out_dtype=torch.float, **tens)
+    mir_full = Mirror(None, k, n, bias=bias, out_dtype=torch.float, **tens)
+    exported = ref_full.tp_export(None, Producer())
+    ctx = {"consumer": Consumer(), "device": "cpu"}
+    world = 3
+    splits = [(True, a, b) for (a, b) in tp.split_ranges(n, world)] + [(False, a, b) for (a, b) in tp.split_ranges(k, world)] + [None]
+    for split in splits:
+        r = ref_mod.LinearEXL3.tp_import_split(ctx, exported, None, split)
+        m = mir_full.tp_slice(split)
+        assert (r.in_features, r.out_features, r.K, r.mcg, r.mul1, r.out_dtype) == (m.in_features, m.out_features, m.K, m.mcg, m.mul1, m.out_dtype)
+        assert torch.equal(r.trellis, m.trellis) and torch.equal(r.suh, m.suh) and torch.equal(r.svh, m.svh)
+        assert (r.bias is None) == (m.bias is None) and (r.bias is None or torch.equal(r.bias, m.bias))
+        assert m.trellis.is_contiguous()
