@@ -131,7 +131,7 @@ def test_every_reference_call_site_of_the_qgemm_surface_fits_the_shim():
     sigs = {o: inspect.signature(getattr(ext, o)) for o in ops}
     seen = {o: 0 for o in ops}
     files = 0
-    for root, _, names in os.walk(REF):
+    for root, _, names in os.walk(os.path.dirname(REF)):            # the package, science/ (qgemm_benchmark.py), tests/, eval/
         if "exllamav3_ext" in root:
             continue
         for nm in names:
@@ -155,6 +155,7 @@ def test_every_reference_call_site_of_the_qgemm_surface_fits_the_shim():
                         raise AssertionError(f"{path}:{node.lineno}: ext.{op} call does not fit the shim: {e}")
                     seen[op] += 1
     assert files > 50
+    assert seen["exl3_gemm"] >= 1 and seen["exl3_gemm_num_kernel_shapes"] >= 1 and seen["exl3_gemm_shape_compat"] >= 1   # science/qgemm_benchmark.py
     # the call sites SURVEY.md 8b names exist and were checked
     assert seen["exl3_mgemm"] >= 8 and seen["hgemm"] >= 3 and seen["had_r_128"] >= 2 and seen["reconstruct"] >= 2
     assert seen["reconstruct_had_slice"] >= 2 and seen["reconstruct_slice"] >= 1 and seen["exl3_gemv_int8_max_k"] >= 1
