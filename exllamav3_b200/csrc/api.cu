@@ -179,10 +179,17 @@ int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed, cons
 // m <= 2 is its int8 GEMV, exl3_gemm.cu:182-186), else the bit-exact tcgen05 path; exl3b_set_gemm_path overrides.
 // Rows 5..8 exist on the int8 path (forced) but are not selected automatically yet: its per-unit digit warps are the
 // pacing role there (measured 25 us vs 19 us for the exact path on 4096 x 4096 at m = 8).
-static int select_gemm_path(const GemmArgs& g)
+static int select_gemm_path(const GemmArgs& g, int force_shape_idx = -1)
 {
     int path = g_force_path.load();
     if (path == EXL3B_TAG_TC_I8_ROUTED) path = 0;            // only concerns exl3b_mgemm
+    // per-call kernel choice, the role of the reference's force_shape_idx (exl3_gemm.cuh:28; science/qgemm_benchmark.py times
+    // every "shape" 1..exl3_gemm_num_kernel_shapes() this way): 1 = CUDA-core twin, 2 = exact tcgen05 kernel; <= 0 = automatic
+    if (force_shape_idx > 0)
+    {
+        EXL3B_CHECK(force_shape_idx <= 2, EXL3B_ERR_ARG, "exl3_gemm: force_shape_idx %d out of range (1 = CUDA-core, 2 = tcgen05)", force_shape_idx);
+        path = force_shape_idx == 1 ? EXL3B_TAG_SIMT : EXL3B_TAG_TC;
+    }
     if (path == EXL3B_TAG_TC_I8)
         EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4, or m <= 8 with m * k <= 32768)");
     if (path == EXL3B_TAG_TC)
@@ -234,9 +241,9 @@ int exl3b_plan_cta_of_unit(int64_t units, int grid, int64_t unit)
 int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void* suh, void* A_had, const void* svh,
                int m, int k, int n, int K, int cb, int c_fp32, int force_shape_idx, int force_num_sms)
 {
-    (void) force_shape_idx;
     cudaStream_t stream = (cudaStream_t) stream_;
     int r = check_kcb(K, cb); if (r) return r;
+    EXL3B_CHECK(force_shape_idx <= 2, EXL3B_ERR_ARG, "exl3_gemm: force_shape_idx %d out of range (1 = CUDA-core, 2 = tcgen05)", force_shape_idx);
     EXL3B_CHECK(m >= 0 && k >= 0 && n >= 0, EXL3B_ERR_SHAPE, "exl3_gemm: negative size");
     EXL3B_CHECK(k % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: k (%d) must be divisible by 128", k);
     EXL3B_CHECK(n % 128 == 0, EXL3B_ERR_SHAPE, "exl3_gemm: n (%d) must be divisible by 128", n);
@@ -249,7 +256,7 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
     g.m = m; g.k = k; g.n = n; g.K = K; g.cb = cb; g.c_fp32 = c_fp32 != 0; g.out_scale = 1.0f;
     g.max_ctas = force_num_sms > 0 ? force_num_sms : 0;
 
-    int path = select_gemm_path(g);
+    int path = select_gemm_path(g, force_shape_idx);
     if (path < 0) return path;
     if (path == EXL3B_TAG_TC_I8) return launch_gemm_tc_i8(stream, ctx, g);
     if (path == EXL3B_TAG_TC) return launch_gemm_tc(stream, ctx, g);

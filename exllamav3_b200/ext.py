@@ -425,7 +425,9 @@ def exl3_gemv_int8_max_k(device: int) -> int:
 
 
 def exl3_gemm_num_kernel_shapes() -> int:
-    """The reference enumerates 4 mma.sync tile shapes (exl3_kernel_map.cuh:53-60); here: SIMT and tcgen05 paths."""
+    """The reference enumerates 4 mma.sync tile shapes (exl3_kernel_map.cuh:53-60) that force_shape_idx selects; here the
+    selectable kernels are 1 = CUDA-core twin, 2 = exact tcgen05 kernel (exl3_gemm honours force_shape_idx 1 / 2 per call);
+    the int8 tensor-core path is what automatic selection (-1) adds for mul1 at <= 4 rows."""
     return 2
 
 

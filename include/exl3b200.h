@@ -101,8 +101,9 @@ int exl3b_plan_cta_of_unit(int64_t units, int grid, int64_t unit);
  *   A_had  (m, k) fp16 scratch for the transformed input; may alias A; may be NULL (library scratch is used)
  *   svh    (n) fp16 or NULL (NULL: no output transform)
  *   k % 128 == 0, n % 128 == 0, 1 <= K <= 8.
- *   force_shape_idx, force_num_sms: accepted for signature parity (exl3_gemm.cuh:28,32); > 0 values are honoured
- *   only where they have a meaning here (force_num_sms caps the persistent grid).
+ *   force_shape_idx (exl3_gemm.cuh:28): <= 0 automatic; 1 = CUDA-core twin, 2 = exact tcgen05 kernel for THIS call (what
+ *   science/qgemm_benchmark.py uses to time every kernel "shape"); larger values are an error.
+ *   force_num_sms (exl3_gemm.cuh:32): > 0 caps the persistent grid.
  */
 int exl3b_gemm(void* stream,
                const void* A, const void* B, void* C,

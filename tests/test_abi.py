@@ -150,3 +150,15 @@ def test_mgemm_split_host_logic(monkeypatch):
     n_before = len(ext._table_cache); del B, su, sv
     import gc; gc.collect()
     assert len(ext._table_cache) <= n_before - 3
+
+
+def test_force_shape_idx_validation_without_gpu():
+    """force_shape_idx selects the kernel per call like the reference's (1 = CUDA-core twin, 2 = exact tcgen05); an index
+    beyond exl3_gemm_num_kernel_shapes() is an argument error raised before any CUDA work."""
+    from exllamav3_b200 import ext
+    one = ctypes.c_void_p(16)
+    assert ext.exl3_gemm_num_kernel_shapes() == 2
+    assert ext.lib.exl3b_gemm(None, one, one, one, one, one, one, 1, 128, 128, 4, 2, 0, 3, 0) == -2
+    assert b"force_shape_idx 3 out of range" in ext.lib.exl3b_last_error()
+    assert ext.exl3_gemm_shape_compat(1, 1, 4096, 4096, 4) and ext.exl3_gemm_shape_compat(2, 32, 4096, 4096, 4)
+    assert not ext.exl3_gemm_shape_compat(3, 1, 4096, 4096, 4) and not ext.exl3_gemm_shape_compat(1, 1, 4000, 4096, 4)
