@@ -247,11 +247,11 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
       decode_hbm      per matrix shape of the model, the batch-1 qgemm's achieved HBM GB/s = algorithmic bytes /
                       launch time, from one CUDA-graph replay of that shape's 32 layer instances back to back (distinct weight
                       buffers, 67-940 MB per shape; weights are loaded evict-first), CUDA events on the launching stream
-      prefill_tensor  the prefill sibling of the same linear (reconstruct_had + tcgen05 dense GEMM, LinearEXL3.forward for
+      prefill_tensor  the prefill sibling of the same linear (reconstruct_had + tcgen05 dense GEMM, QLinear.forward for
                       rows > 144) at batch 32 x 2048 rows: achieved TFLOP/s (2 m k n) against the measured dense bf16 peaks
     """
     import torch
-    from exllamav3_b200 import ext, LinearEXL3
+    from exllamav3_b200 import ext, QLinear
     out = {"decode_hbm": {}, "prefill_tensor": {}}
     by_name = {}
     for mt in tok.mats:
@@ -296,7 +296,7 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
     h = cfg["hidden"]
     for (k, n, m) in ((h, cfg["q"], 32 * 2048), (h, cfg["inter"], 8 * 2048)):
         mt = next(t for t in tok.mats if t["k"] == k and t["n"] == n)
-        lin = LinearEXL3(None, k, n, suh=mt["suh"], svh=mt["svh"], trellis=mt["tr"], mul1=torch.zeros((), dtype=torch.int, device=dev))
+        lin = QLinear(mt["tr"], mt["suh"], mt["svh"], mul1=True)
         x = torch.randn((m, k), generator=gen, device=dev).half()
         with torch.cuda.stream(stream):
             for _ in range(2):

@@ -10,8 +10,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libexl3b200.so")
+# EXL3B_LIB_SUFFIX=_dbg builds a second library (own object directory) next to the production one, e.g. the bring-up build
+# with in-kernel timeline stamps: EXL3B_LIB_SUFFIX=_dbg EXL3B_TC_DEBUG=1 python -m exllamav3_b200.build; ext.py loads it when
+# EXL3B_LIBRARY points at it.
+_SUFFIX = os.environ.get("EXL3B_LIB_SUFFIX", "")
+OBJ = os.path.join(HERE, "build" + _SUFFIX)
+LIB = os.path.join(HERE, f"libexl3b200{_SUFFIX}.so")
 
 SOURCES = ["api.cu", "kernels_basic.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_i8.cu", "gemm_tc_i8_ar.cu", "gemm_tc_i8_routed.cu", "hgemm.cu", "hgemm_tc.cu"]
 HEADERS = ["common.cuh", "decode.cuh", "epilogue.cuh", "ptx.cuh", "tc_common.cuh", "gemm_tc_i8_body.cuh", "i8_math.cuh", os.path.join("..", "..", "include", "exl3b200.h")]

@@ -58,6 +58,12 @@ int get_ctx(DevCtx** out)
         EXL3B_CUDA(cudaMalloc(&c.tmap_slots, (size_t) DevCtx::NUM_SLOTS * DevCtx::TMAP_SLOTS * 128));
         EXL3B_CUDA(cudaMalloc(&c.i8_parts, (size_t) DevCtx::NUM_SLOTS * DevCtx::I8_PART_CTAS * 1024 * sizeof(float)));
         EXL3B_CUDA(cudaMemset(c.i8_parts, 0xff, (size_t) DevCtx::NUM_SLOTS * DevCtx::I8_PART_CTAS * 1024 * sizeof(float)));
+        // tiled / plain transformed activations: one pass of the exact tcgen05 path is <= 256 rows (gemm_tc.cu)
+        c.xh_tiled_slot_bytes = (size_t) 2 * 256 * DevCtx::XH_MAX_K;
+        EXL3B_CUDA(cudaMalloc(&c.xh_tiled, c.xh_tiled_slot_bytes * DevCtx::XH_SLOTS));
+        EXL3B_CUDA(cudaMemset(c.xh_tiled, 0, c.xh_tiled_slot_bytes * DevCtx::XH_SLOTS));
+        c.xh_scratch_elems = (size_t) 256 * DevCtx::XH_MAX_K;
+        EXL3B_CUDA(cudaMalloc(&c.xh_scratch, c.xh_scratch_elems * sizeof(half)));
         EXL3B_CUDA(cudaDeviceSynchronize());
         c.device = dev;
     }
@@ -65,27 +71,22 @@ int get_ctx(DevCtx** out)
     return 0;
 }
 
+// Library scratch is allocated ONCE per device (get_ctx) at a fixed worst-case size and never freed or moved: a CUDA graph
+// captured earlier keeps replaying with these addresses, and nothing here may synchronise or allocate inside a launch path
+// (the reference has the same rule for its workspaces, exl3_gemv_int8.cu:93-99).  A call that needs more than the fixed
+// size is refused (EXL3B_ERR_UNSUPPORTED); exl3_gemm callers that pass their own A_had never touch xh_scratch.
 int ensure_xh_scratch(DevCtx* ctx, size_t elems)
 {
-    if (ctx->xh_scratch_elems >= elems) return 0;
-    // growing is rare (first call / larger m); synchronise so no in-flight kernel still reads the old buffer
-    EXL3B_CUDA(cudaDeviceSynchronize());
-    if (ctx->xh_scratch) cudaFree(ctx->xh_scratch);
-    size_t want = elems < (1u << 20) ? (1u << 20) : elems;
-    EXL3B_CUDA(cudaMalloc(&ctx->xh_scratch, want * sizeof(half)));
-    ctx->xh_scratch_elems = want;
+    EXL3B_CHECK(elems <= ctx->xh_scratch_elems, EXL3B_ERR_UNSUPPORTED,
+                "exl3_gemm: A_had = NULL needs %zu scratch elements, the library holds %zu (pass A_had)", elems, ctx->xh_scratch_elems);
     return 0;
 }
 
 int ensure_xh_tiled(DevCtx* ctx, size_t bytes_per_slot)
 {
-    if (ctx->xh_tiled_slot_bytes >= bytes_per_slot) return 0;
-    EXL3B_CUDA(cudaDeviceSynchronize());
-    if (ctx->xh_tiled) cudaFree(ctx->xh_tiled);
-    size_t want = bytes_per_slot < (4u << 20) ? (4u << 20) : (bytes_per_slot + 1023) / 1024 * 1024;
-    EXL3B_CUDA(cudaMalloc(&ctx->xh_tiled, want * DevCtx::XH_SLOTS));
-    EXL3B_CUDA(cudaMemset(ctx->xh_tiled, 0, want * DevCtx::XH_SLOTS));
-    ctx->xh_tiled_slot_bytes = want;
+    EXL3B_CHECK(bytes_per_slot <= ctx->xh_tiled_slot_bytes, EXL3B_ERR_UNSUPPORTED,
+                "exl3_gemm: %zu bytes of tiled activations per pass exceed the library's fixed buffer (%zu: 256 rows x k <= %d)",
+                bytes_per_slot, ctx->xh_tiled_slot_bytes, DevCtx::XH_MAX_K);
     return 0;
 }
 
@@ -339,8 +340,10 @@ int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, co
     const int path = g_force_path.load();
     if ((path == EXL3B_TAG_TC_I8 || path == EXL3B_TAG_TC_I8_ROUTED || (path == 0 && m <= 4)) && mgemm_tc_i8_supported(ctx, a))
         return launch_mgemm_tc_i8((cudaStream_t) stream, ctx, a);
-    // routed / weighted calls (MoE decode) on the tensor-core path: opt-in until verified on hardware
-    if (path == EXL3B_TAG_TC_I8_ROUTED && mgemm_tc_i8_routed_supported(ctx, a))
+    // routed / weighted calls (MoE decode: indices, weights, expert-range filter) with mul1 at <= 4 rows: the tensor-core
+    // kernel with one CTA group per active slot (verified on hardware in round 2; EXL3B_TAG_SIMT still forces the CUDA-core twin)
+    if ((path == 0 || path == EXL3B_TAG_TC_I8 || path == EXL3B_TAG_TC_I8_ROUTED) && (a.indices || a.weights || a.min_index >= 0)
+        && mgemm_tc_i8_routed_supported(ctx, a))
         return launch_mgemm_tc_i8_routed((cudaStream_t) stream, ctx, a);
     return launch_mgemm((cudaStream_t) stream, ctx, a);
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/exl3b200.h"
 
 namespace exl3b {
@@ -44,9 +45,10 @@ struct DevCtx
     int* counters = nullptr;      // NUM_SLOTS * COUNTERS_PER_SLOT, zero-initialised once
     MSlotTable* tabs = nullptr;   // NUM_SLOTS mgemm slot tables
     static constexpr int XH_SLOTS = 4;
-    uint8_t* xh_tiled = nullptr;  // XH_SLOTS tiled activation buffers for the tcgen05 path
+    static constexpr int XH_MAX_K = 65536;  // largest in_features the fixed activation scratch below is sized for
+    uint8_t* xh_tiled = nullptr;  // XH_SLOTS tiled activation buffers for the tcgen05 path (256 rows x XH_MAX_K fp16 each), allocated once
     size_t xh_tiled_slot_bytes = 0;
-    half* xh_scratch = nullptr;   // input-transform scratch when the caller passes A_had = NULL
+    half* xh_scratch = nullptr;   // input-transform scratch when the caller passes A_had = NULL (256 x XH_MAX_K), allocated once
     size_t xh_scratch_elems = 0;
     uint8_t* tmap_slots = nullptr;   // NUM_SLOTS x TMAP_SLOTS x 128 B: per-CTA patched tensor maps of multi-matrix launches
     static constexpr int TMAP_SLOTS = 256;
@@ -56,8 +58,12 @@ struct DevCtx
     float* i8_parts = nullptr;
     static constexpr int I8_PART_CTAS = 256;
     float* i8_parts_slot(int s) { return i8_parts + (size_t) s * I8_PART_CTAS * 1024; }
-    uint64_t launch_seq = 0;
-    int next_slot() { return (int) (launch_seq++ % NUM_SLOTS); }
+    // Launch slots rotate per device, not per stream: launches issued concurrently on two streams of one device (or from two
+    // host threads: ctypes releases the GIL) get distinct slots from this atomic counter, but more than NUM_SLOTS launches in
+    // flight on one device would share split-K scratch -- the library supports ONE in-order stream of qgemm launches per
+    // device at a time, like the reference (single DevCtx lock buffer, exl3_devctx.cuh:35; include/exl3b200.h "Threading").
+    std::atomic<uint64_t> launch_seq{0};
+    int next_slot() { return (int) (launch_seq.fetch_add(1, std::memory_order_relaxed) % NUM_SLOTS); }
     float* ws_slot(int s) { return (float*) ((char*) ws + (size_t) s * WS_BYTES_PER_SLOT); }
     int* counter_slot(int s) { return counters + (size_t) s * COUNTERS_PER_SLOT; }
     MSlotTable* tab_slot(int s) { return tabs + s; }

@@ -460,7 +460,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 int get_weight_tmap(const void* B, int k, int n, int K, CUtensorMap* out)
 {
+#ifdef EXL3B_TC_DEBUG
     const bool flat = (g_tc_knob & 16) != 0;     // experiment: contiguous 8-row boxes (wrong data, same bytes)
+#else
+    constexpr bool flat = false;
+#endif
     static PFN_encodeTiled encode = nullptr;
     static std::mutex mu;
     struct Key { const void* p; int k, n, K; bool operator==(const Key& o) const { return p == o.p && k == o.k && n == o.n && K == o.K; } };
@@ -527,8 +531,15 @@ static void tc_launch_v(cudaStream_t stream, int grid, int smem_bytes, const TcP
 
 unsigned long long* g_tc_dbg = nullptr;
 int g_tc_knob = 0;
+// bring-up hooks: live only in the EXL3B_TC_DEBUG build (libexl3b200_dbg.so); the production library ignores them, so no
+// exported call can change what its kernels compute
+#ifdef EXL3B_TC_DEBUG
 void tc_set_debug_buffer(unsigned long long* d) { g_tc_dbg = d; }
 void tc_set_knob(int k) { g_tc_knob = k; }
+#else
+void tc_set_debug_buffer(unsigned long long*) { }
+void tc_set_knob(int) { }
+#endif
 
 bool gemm_tc_supported(const GemmArgs& a)
 {

@@ -555,12 +555,15 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
         {
             if (et == 0)
             {
-                const unsigned int e = ld_relaxed_gpu_u32(ar->state);
-                const unsigned int ticket = atomicAdd(ar->state + 1, 1u);
+                // ordering: the epoch load must be performed before this CTA's ticket is visible (otherwise the last ticket
+                // holder could already have advanced the epoch and this CTA would pick the other slot than its peers): acquire
+                // load, acq_rel ticket; the advance is a release store after the ticket reset
+                const unsigned int e = ld_acquire_gpu_u32(ar->state);
+                const unsigned int ticket = atom_add_acq_rel_gpu_u32(ar->state + 1, 1u);
                 if (ticket == gridDim.x - 1)
                 {
                     st_relaxed_gpu_u32(ar->state + 1, 0u);
-                    st_relaxed_gpu_u32(ar->state, e + 1u);
+                    st_release_gpu_u32(ar->state, e + 1u);
                 }
                 *s_ar = e;
             }

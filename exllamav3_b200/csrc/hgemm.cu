@@ -60,12 +60,12 @@ hgemm_simt_kernel(const half* __restrict__ a, const half* __restrict__ b, void* 
 
 int launch_hgemm_tc(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,
                     int64_t c_stride);
-bool hgemm_tc_supported(int m, int k, int n, int64_t c_stride);
+bool hgemm_tc_supported(const void* a, const void* b, const void* c, int m, int k, int n, int64_t c_stride);
 
 int launch_hgemm(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,
                  int64_t c_stride)
 {
-    if (hgemm_tc_supported(m, k, n, c_stride))
+    if (hgemm_tc_supported(a, b, c, m, k, n, c_stride))
         return launch_hgemm_tc(stream, a, b, c, m, k, n, c_fp32, c_stride);
     dim3 grid((n + 63) / 64, (m + 63) / 64);
     if (c_fp32) hgemm_simt_kernel<true><<<grid, 256, 0, stream>>>(a, b, c, m, k, n, c_stride);

@@ -235,10 +235,12 @@ static int make_tmap_fp16_2d(const void* base, uint64_t inner, uint64_t outer, u
     return 0;
 }
 
-bool hgemm_tc_supported(int m, int k, int n, int64_t c_stride)
+bool hgemm_tc_supported(const void* a, const void* b, const void* c, int m, int k, int n, int64_t c_stride)
 {
-    // TMA needs 16-byte aligned row pitches; the epilogue stores 16-byte vectors
-    return m >= 1 && k >= 8 && n >= 8 && k % 8 == 0 && n % 8 == 0 && c_stride % 8 == 0;
+    // TMA needs 16-byte aligned bases and row pitches; the epilogue stores 16-byte vectors.  Anything else (e.g. an
+    // unaligned view) takes the CUDA-core kernel instead of an error.
+    const bool aligned = (((uintptr_t) a | (uintptr_t) b | (uintptr_t) c) & 15) == 0;
+    return aligned && m >= 1 && k >= 8 && n >= 8 && k % 8 == 0 && n % 8 == 0 && c_stride % 8 == 0;
 }
 
 int launch_hgemm_tc(cudaStream_t stream, const half* a, const half* b, void* c, int m, int k, int n, bool c_fp32,

@@ -146,6 +146,22 @@ __device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu_u32(uint32_t* p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 
 // ---- relaxed system-scope vector accesses (flag-in-data exchange between GPUs over NVLink peer memory) -------------------
 // A vector access is a set of 32-bit accesses, each of them single-copy atomic: every word is its own flag.

@@ -18,7 +18,9 @@ import ctypes, os, weakref
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libexl3b200.so")
+# EXL3B_LIBRARY selects another build of the SAME library (e.g. the bring-up build with in-kernel timeline stamps); never a
+# different implementation
+_LIB_PATH = os.environ.get("EXL3B_LIBRARY") or os.path.join(_HERE, "libexl3b200.so")
 
 if not os.path.exists(_LIB_PATH):
     raise ImportError(

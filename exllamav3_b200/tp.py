@@ -2,7 +2,7 @@
 Tensor-parallel shard + collective plumbing around the EXL3 linear -- the part of the reference's TP machinery that
 touches the qgemm path:
 
-  * shard construction: LinearEXL3.tp_import_split slicing rules (modules/quant/exl3.py:284-330) via LinearEXL3.tp_slice
+  * shard construction: LinearEXL3.tp_import_split slicing rules (modules/quant/exl3.py:284-330) as the free function tp_slice
   * partition: q/k/v/gate/up column-parallel, o/down row-parallel, 128-channel granularity (modules/linear.py:645-656)
   * one all-reduce (sum) per row-parallel output, called by the CALLER of the linear (modules/mlp.py:769-770,
     modules/attn.py:546-547) -- here `row_parallel_forward`.
@@ -39,14 +39,42 @@ def split_ranges(total: int, parts: int, granularity: int = GRANULARITY):
     return out
 
 
+def tp_slice(lin, split, device=None):
+    """
+    Shard [first, last) of a QLinear, channels in multiples of 128 (both Hadamards are block-diagonal over 128 channels and
+    suh / svh are per channel, so a shard is again a complete EXL3 linear).  split = (split_out, first, last):
+      column shard (split_out = True)   trellis[:, first/16:last/16], svh[first:last], bias[first:last]; suh whole
+      row shard    (split_out = False)  trellis[first/16:last/16], suh[first:last]; svh whole; the bias goes to the shard
+                                        that starts at 0 only (it must be added once to the summed output)
+    -- the slicing of the reference's tp_import_split (modules/quant/exl3.py:284-330), without its shared-memory transport.
+    Every shard records whether ANY shard of the linear carries a bias (`bias_in_group`), so that all ranks pick the same
+    collective in row_parallel_forward.
+    """
+    from .qlinear import QLinear
+    split_out, first, last = split if split is not None else (True, 0, lin.out_features)
+    if first % GRANULARITY or last % GRANULARITY:
+        raise ValueError("tensor-parallel split granularity is 128 channels")
+    dev = device or lin.trellis.device
+    put = lambda t: None if t is None else t.to(dev).contiguous()
+    t0, t1 = first // 16, last // 16
+    if split_out:
+        tr, suh, svh = lin.trellis[:, t0:t1, :], lin.suh, lin.svh[first:last]
+        bias = None if lin.bias is None else lin.bias[first:last]
+    else:
+        tr, suh, svh = lin.trellis[t0:t1], lin.suh[first:last], lin.svh
+        bias = lin.bias if first == 0 else None
+    return QLinear(put(tr), put(suh), put(svh), mcg=lin.mcg, mul1=lin.mul1, bias=put(bias), out_dtype=lin.out_dtype,
+                   bias_in_group=lin.bias is not None)
+
+
 def column_shard(lin, rank: int, world: int, device=None):
     first, last = split_ranges(lin.out_features, world)[rank]
-    return lin.tp_slice((True, first, last), device)
+    return tp_slice(lin, (True, first, last), device)
 
 
 def row_shard(lin, rank: int, world: int, device=None):
     first, last = split_ranges(lin.in_features, world)[rank]
-    return lin.tp_slice((False, first, last), device)
+    return tp_slice(lin, (False, first, last), device)
 
 
 def all_reduce(t: torch.Tensor, group=None) -> torch.Tensor:
@@ -86,9 +114,12 @@ def disable_fused_allreduce(group=None) -> None:
 
 
 def fused_allreduce_eligible(shard, rows: int, any_bias: bool = False) -> bool:
-    """Pure host logic (no device): would row_parallel_forward take the one-kernel path for this call?"""
+    """Pure host logic (no device): would row_parallel_forward take the one-kernel path for this call?  The answer must be
+    the same on every rank (a rank on the NCCL path while its peers wait in the fused kernel is a hang), so it depends only
+    on rank-invariant facts: the shard's shape / codebook, the group, and `bias_in_group` -- never on whether THIS shard
+    happens to hold the bias (only the first row shard does)."""
     from . import ext
-    if not _fused["on"] or any_bias or shard.bias is not None:
+    if not _fused["on"] or any_bias or getattr(shard, "bias_in_group", shard.bias is not None):
         return False
     return ext.exl3_gemm_allreduce_supported(rows, shard.in_features, shard.out_features, shard.K, shard.mcg, shard.mul1,
                                              _fused["world"], _fused["max_elems"])
@@ -98,13 +129,13 @@ def row_parallel_forward(shard, x_local: torch.Tensor, params: dict, out_dtype=N
                          any_bias: bool = False) -> torch.Tensor:
     """
     y = sum over ranks of shard(x[:, first:last]): each rank applies its own full epilogue to its partial, one sum.
-    `any_bias`: some rank's shard carries the bias (the reference gives it to the first shard only, exl3.py:318-321), which
-    keeps the call on the NCCL path.
+    A bias anywhere in the group (shard.bias_in_group, recorded by tp_slice on every rank; `any_bias` forces it) keeps the
+    call on the NCCL path on ALL ranks.
     """
     rows = x_local.numel() // x_local.shape[-1]
     if not params.get("reconstruct") and fused_allreduce_eligible(shard, rows, any_bias):
         from . import ext
-        dtype = out_dtype or shard.default_out_dtype
+        dtype = out_dtype or shard.out_dtype
         y = torch.empty(tuple(x_local.shape[:-1]) + (shard.out_features,), dtype=dtype, device=x_local.device)
         ext.exl3_gemm_allreduce(x_local.view(-1, x_local.shape[-1]), shard.trellis, y.view(-1, shard.out_features),
                                 shard.suh, None, shard.svh, shard.mcg, shard.mul1)

@@ -10,8 +10,17 @@
  *   - plain pointers and sizes only: no torch / ATen types cross this boundary.
  *   - every `const void*` / `void*` tensor argument is a DEVICE pointer on the current CUDA device unless the
  *     name ends in `_host`.  `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
- *   - the caller owns all buffers.  The library lazily allocates per-device scratch (split-K partials,
- *     tile counters) with cudaMalloc on first use, like the reference's DevCtx (exllamav3_ext/quant/exl3_devctx.cu:24-70).
+ *   - the caller owns all buffers.  The library allocates its per-device scratch (split-K partials, tile counters,
+ *     transformed-activation buffers for in_features <= 65536) with cudaMalloc ONCE, on the first call on a device, like the
+ *     reference's DevCtx (exllamav3_ext/quant/exl3_devctx.cu:24-70); it is never freed, moved or grown afterwards, so a
+ *     CUDA graph captured over these entry points stays valid, and no entry point allocates or synchronises once the device
+ *     context exists (make the first call on a device OUTSIDE stream capture).
+ *   - Threading / streams: the scratch is per DEVICE and shared by all streams; launches rotate through 8 scratch slots, so
+ *     the supported pattern is one in-order stream of qgemm launches per device at a time (what the reference supports as
+ *     well: one lock buffer per device, exl3_devctx.cuh:35, ops called with the GIL held).  Calls from several host threads
+ *     are safe as far as the slot rotation goes (atomic), but more than 8 launches in flight on one device across streams
+ *     may share split-K scratch and is undefined.  In-kernel watchdogs (4 s split-K, 20 s tensor-parallel exchange) print
+ *     and trap instead of hanging the GPU; a trap is a sticky CUDA error like the reference's exit-on-error (util.cuh:92-100).
  *   - return value: >= 0 on success (exl3b_gemm / exl3b_mgemm return a kernel-path tag like the reference's
  *     exl3_gemm, exllamav3_ext/quant/exl3_gemm.cu:234,247,308), < 0 = -(enum exl3b_status).  On error nothing was launched
  *     and exl3b_last_error() describes the problem (the reference raises via TORCH_CHECK, exllamav3_ext/util.h:24-37;
@@ -46,7 +55,7 @@ enum exl3b_status
 #define EXL3B_TAG_SIMT 100     /* CUDA-core bring-up kernel                                */
 #define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
 #define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path: mul1, m <= 4 (auto); m <= 8 with m*k <= 32768 when forced */
-#define EXL3B_TAG_TC_I8_ROUTED 212 /* routed / weighted exl3b_mgemm (MoE decode) on the kind::i8 kernel; taken only when forced (opt-in) */
+#define EXL3B_TAG_TC_I8_ROUTED 212 /* routed / weighted exl3b_mgemm (MoE decode) on the kind::i8 kernel: mul1, m <= 4 (auto) */
 #define EXL3B_TAG_TC_I8_AR 211 /* the same kernel with the tensor-parallel sum fused into its epilogue (exl3b_gemm_allreduce) */
 
 int exl3b_abi_version(void);

@@ -81,21 +81,21 @@ def test_use_mgemm_policy_through_the_shim():
 
 def test_linear_exl3_tp_slice_host_logic():
     # slicing rules of LinearEXL3.tp_import_split (modules/quant/exl3.py:284-330) on CPU tensors: no kernels run
-    from exllamav3_b200 import LinearEXL3
+    from exllamav3_b200 import QLinear, tp
     from oracle import exl3_oracle as orc
     k, n, K = 256, 384, 3
     tr, suh, svh, _ = orc.make_synthetic(k, n, K)
     bias = torch.arange(n, dtype=torch.half)
-    lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh),
-                     trellis=torch.from_numpy(tr), mul1=torch.zeros((), dtype=torch.int), bias=bias)
-    col = lin.tp_slice((True, 128, 384))
+    lin = QLinear(torch.from_numpy(tr), torch.from_numpy(suh), torch.from_numpy(svh), mul1=True, bias=bias)
+    col = tp.tp_slice(lin, (True, 128, 384))
     assert col.in_features == k and col.out_features == 256
     assert torch.equal(col.trellis, lin.trellis[:, 8:24, :]) and torch.equal(col.svh, lin.svh[128:384])
     assert torch.equal(col.suh, lin.suh) and torch.equal(col.bias, bias[128:384]) and col.mul1 and not col.mcg
-    row0 = lin.tp_slice((False, 0, 128)); row1 = lin.tp_slice((False, 128, 256))
+    row0 = tp.tp_slice(lin, (False, 0, 128)); row1 = tp.tp_slice(lin, (False, 128, 256))
     assert row0.in_features == 128 and row0.out_features == n
     assert torch.equal(row1.trellis, lin.trellis[8:16]) and torch.equal(row1.suh, lin.suh[128:256])
     assert row0.bias is not None and row1.bias is None            # bias only on the shard with first == 0
+    assert row0.bias_in_group and row1.bias_in_group and col.bias_in_group     # ... but every shard knows the group has one
     assert col.trellis.is_contiguous() and row1.trellis.is_contiguous()
 
 

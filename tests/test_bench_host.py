@@ -90,7 +90,7 @@ def test_qgemm_section_control_flow(monkeypatch):
     Python control flow, the shapes it times and the keys it reports -- so that a typo cannot cost the round's bench line."""
     import contextlib
     import exllamav3_b200
-    from exllamav3_b200 import ext, LinearEXL3
+    from exllamav3_b200 import ext, QLinear
 
     class Ev:
         def __init__(self, enable_timing=True): pass
@@ -110,7 +110,7 @@ def test_qgemm_section_control_flow(monkeypatch):
     monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
     monkeypatch.setattr(torch.cuda, "Event", Ev)
     monkeypatch.setattr(ext, "exl3_gemm", lambda *a: calls.append(("gemm", a[0].shape[-1], a[2].shape[-1])) or 210)
-    monkeypatch.setattr(LinearEXL3, "forward", lambda self, x, params, out_dtype=None: calls.append(("prefill", tuple(x.shape), self.out_features)) or x)
+    monkeypatch.setattr(QLinear, "forward", lambda self, x, params, out_dtype=None: calls.append(("prefill", tuple(x.shape), self.out_features)) or x)
     tok = bench.Token(TINY, 1, 0, torch.device("cpu"))
     out = bench.qgemm_section(tok, TINY, Stream(), 6576.1)
     assert set(out["decode_hbm"]) == {"q", "k", "v", "o", "gate", "up", "down", "lm_head"}

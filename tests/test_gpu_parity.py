@@ -197,11 +197,10 @@ def test_hgemm(cuda):
 
 def test_linear_exl3_kernel_vs_reconstruct_path(cuda):
     # the reference's own pin of this path: tests/test_qgemm.py:31-53 (rtol = atol = 0.05), m list from there
-    from exllamav3_b200 import LinearEXL3
+    from exllamav3_b200 import QLinear
     K, k, n = 3, 1024, 512
     tr, suh, svh, _ = orc.make_synthetic(k, n, K)
-    lin = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
-                     mul1=torch.zeros((), dtype=torch.int, device=cuda))
+    lin = QLinear(T(tr, cuda), T(suh, cuda), T(svh, cuda), mul1=True)
     torch.manual_seed(0)
     for m in (1, 2, 8, 16, 17, 31, 32, 33, 256, 2048):
         x = torch.randn((1, m, k), dtype=torch.half, device=cuda)
@@ -214,24 +213,24 @@ def test_linear_exl3_kernel_vs_reconstruct_path(cuda):
         assert mx <= 5e-3 and rms <= 2e-3, (m, mx, rms)
     # fp32 output + bias
     bias = torch.randn(n, dtype=torch.half, device=cuda)
-    lin2 = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
-                      mul1=torch.zeros((), dtype=torch.int, device=cuda), bias=bias, out_dtype=torch.float)
+    lin2 = QLinear(T(tr, cuda), T(suh, cuda), T(svh, cuda), mul1=True, bias=bias, out_dtype=torch.float)
     x = torch.randn((4, k), dtype=torch.half, device=cuda)
     y = lin2.forward(x, {})
     assert y.dtype == torch.float
     torch.testing.assert_close(y, lin.forward(x, {}, torch.float) + bias, rtol=1e-3, atol=1e-3)
-    # get_weight_tensor == original-basis W
-    W = lin.get_weight_tensor().cpu().numpy().astype(np.float64)
+    # original-basis W (fused reconstruct kernel)
+    W = lin.weight().cpu().numpy().astype(np.float64)
     Wref = orc.get_weight_tensor_f64(tr, suh, svh, K, 2)
     assert np.abs(W - Wref).max() / np.abs(Wref).max() < 2e-3
 
 
 def test_mgemm_modes(cuda):
-    from exllamav3_b200 import ext, LinearEXL3, MultiLinear
+    from exllamav3_b200 import ext, QLinear, pointer_tables
+    from types import SimpleNamespace
     k, n, K, m, mats, A, wts = gg.mgemm_inputs()
-    lins = [LinearEXL3(None, k, n, suh=T(t[1], cuda), svh=T(t[2], cuda), trellis=T(t[0], cuda),
-                       mul1=torch.zeros((), dtype=torch.int, device=cuda)) for t in mats]
-    ml = MultiLinear(cuda, lins)
+    lins = [QLinear(T(t[0], cuda), T(t[1], cuda), T(t[2], cuda), mul1=True) for t in mats]
+    pt = pointer_tables(cuda, lins)
+    ml = SimpleNamespace(ptrs_trellis=pt[0], ptrs_suh=pt[1], ptrs_svh=pt[2], mcg=False, mul1=True)
     trs = [t[0] for t in mats]; suhs = [t[1] for t in mats]; svhs = [t[2] for t in mats]
     golden = np.load(os.path.join(GOLDEN, "ref_gpu.npz")) if os.path.exists(os.path.join(GOLDEN, "ref_gpu.npz")) else None
     for fp32 in (False, True):
@@ -441,12 +440,11 @@ def test_full_size_properties(cuda):
       * column-split == slice of the full result; row-split partial sums == full result  (TP shard identity, 8e)
       * spot check of 256 random output columns against the fp64 oracle restricted to those columns' 128-blocks
     """
-    from exllamav3_b200 import ext, LinearEXL3
+    from exllamav3_b200 import ext, QLinear, tp
     K, cb = 4, 2
     for (k, n) in ((4096, 4096), (4096, 14336), (14336, 4096)):
         tr, suh, svh, _ = orc.make_synthetic(k, n, K)
-        lin = LinearEXL3(None, k, n, suh=T(suh, cuda), svh=T(svh, cuda), trellis=T(tr, cuda),
-                         mul1=torch.zeros((), dtype=torch.int, device=cuda), out_dtype=torch.float)
+        lin = QLinear(T(tr, cuda), T(suh, cuda), T(svh, cuda), mul1=True, out_dtype=torch.float)
         torch.manual_seed(k + n)
         x1 = torch.randn((1, k), dtype=torch.half, device=cuda); x2 = torch.randn((1, k), dtype=torch.half, device=cuda)
         y1, y2 = lin.forward(x1, {}), lin.forward(x2, {})
@@ -456,11 +454,11 @@ def test_full_size_properties(cuda):
         assert float(lin_err) < 5e-3, (k, n, float(lin_err))
         # TP identities
         half_n = (n // 256) * 128
-        ca = lin.tp_slice((True, 0, half_n)); cb_ = lin.tp_slice((True, half_n, n))
+        ca = tp.tp_slice(lin, (True, 0, half_n)); cb_ = tp.tp_slice(lin, (True, half_n, n))
         ycat = torch.cat((ca.forward(x1, {}), cb_.forward(x1, {})), dim=-1)
         assert float((ycat - y1).abs().max() / y1.abs().max()) < 1e-3
         half_k = (k // 256) * 128
-        ra = lin.tp_slice((False, 0, half_k)); rb = lin.tp_slice((False, half_k, k))
+        ra = tp.tp_slice(lin, (False, 0, half_k)); rb = tp.tp_slice(lin, (False, half_k, k))
         ysum = ra.forward(x1[:, :half_k].contiguous(), {}) + rb.forward(x1[:, half_k:].contiguous(), {})
         assert float((ysum - y1).abs().max() / y1.abs().max()) < 2e-3
         # spot check: two random 128-column blocks against the oracle

@@ -1,16 +1,16 @@
 """
-Host logic of the LinearEXL3 mirror (exllamav3_b200/linear_exl3.py) against the reference's dispatch rules
-(exllamav3/modules/quant/exl3.py:114-218), with a recording stand-in for the extension -- no kernel runs:
-  * forward: rows <= 144 (or no_reconstruct) -> BC_LinearEXL3.run_alloc (the fused qgemm kernel); otherwise, or with
-    params["reconstruct"], the reconstruct -> dense GEMM sibling; per-call override table; contiguity assertion; output dtype
-  * reconstruct_hgemm: unfused sequence below 1024 rows (had_r_128 -> reconstruct -> hgemm -> had_r_128), fused above
-    (reconstruct_had_slice -> hgemm), 32768-column slices for wide outputs with the svh slice and n_offset the kernels expect
+Host logic of QLinear (exllamav3_b200/qlinear.py) against the dispatch rules of the path (the reference's
+exllamav3/modules/quant/exl3.py:114-218 defines them), with a recording stand-in for the extension -- no kernel runs:
+  * forward: rows <= 144 -> BC_LinearEXL3.run_alloc (the fused qgemm kernel); otherwise, or with params["reconstruct"], the
+    materialise -> dense GEMM sibling; contiguity check; output dtype
+  * forward_dense: unfolded sequence below 1024 rows (had_r_128 -> reconstruct -> hgemm -> had_r_128), folded above
+    (reconstruct_had_slice -> hgemm), 32768-column windows for wide outputs with the svh slice and n_offset the kernels expect
 """
 import numpy as np
 import pytest
 import torch
-from exllamav3_b200 import ext, LinearEXL3
-from exllamav3_b200 import linear_exl3 as le
+from exllamav3_b200 import ext, QLinear
+from exllamav3_b200 import qlinear as le
 
 
 class Rec:
@@ -32,8 +32,7 @@ class Rec:
 def _lin(k, n, K=4, **kw):
     g = torch.Generator().manual_seed(0)
     tr = torch.randint(0, 32767, (k // 16, n // 16, 16 * K), generator=g, dtype=torch.int32).to(torch.int16)
-    return LinearEXL3(None, k, n, suh=torch.ones(k, dtype=torch.half), svh=torch.ones(n, dtype=torch.half), trellis=tr,
-                      mul1=torch.zeros((), dtype=torch.int), key="blk.q_proj", **kw)
+    return QLinear(tr, torch.ones(k, dtype=torch.half), torch.ones(n, dtype=torch.half), mul1=True, **kw)
 
 
 def test_forward_dispatch_rules(monkeypatch):
@@ -51,21 +50,18 @@ def test_forward_dispatch_rules(monkeypatch):
     lin.forward(torch.zeros((1, 256), dtype=torch.half), {"reconstruct": True})
     assert rec.names() == ["had_r_128", "reconstruct", "hgemm", "had_r_128"]
     rec.calls.clear()
-    lin.config.infer_params.no_reconstruct = True
-    lin.forward(torch.zeros((4096, 256), dtype=torch.half), {})
+    lin.forward(torch.zeros((4096, 256), dtype=torch.half), {"no_reconstruct": True})
     assert rec.names() == ["exl3_gemm"]
-    lin.config.infer_params.no_reconstruct = False
-    with pytest.raises(AssertionError, match="non-contiguous"):
+    with pytest.raises(ValueError, match="non-contiguous"):
         lin.forward(torch.zeros((4, 512), dtype=torch.half)[:, ::2], {})
     # single rows go through the shared (1, k) scratch, larger inputs get a fresh one (linear.cpp:34-71)
     rec.calls.clear()
     lin.forward(torch.zeros((1, 256), dtype=torch.half), {}); lin.forward(torch.zeros((3, 256), dtype=torch.half), {})
     assert rec.calls[0][5] == (1, 256) and rec.calls[1][5] == (3, 256)                                  # A_had argument
-    # per-call override table
-    class Other:
-        inner = None
-        def forward(self, x, params, out_dtype=None): return "overridden"
-    assert lin.forward(torch.zeros((1, 256), dtype=torch.half), {"ovr": {"blk.q_proj": Other()}}) == "overridden"
+    with pytest.raises(ValueError, match="int16"):
+        QLinear(torch.zeros((16, 16, 64), dtype=torch.int32), lin.suh, lin.svh)
+    with pytest.raises(ValueError, match="do not match"):
+        QLinear(lin.trellis, lin.suh[:128], lin.svh)
 
 
 def test_reconstruct_hgemm_sequences(monkeypatch):
@@ -75,7 +71,7 @@ def test_reconstruct_hgemm_sequences(monkeypatch):
     assert rec.names() == ["reconstruct_had_slice", "hgemm"]                                            # fused above 1024 rows
     assert rec.calls[0][1] == (256, 384) and rec.calls[0][-1] == 0
     # wide outputs (lm_head): slices of at most 32768 columns, svh pre-offset, n_offset passed on
-    monkeypatch.setattr(le, "MAX_RECONSTRUCT_SLICE_N", 256)
+    monkeypatch.setattr(le, "DENSE_WINDOW_COLS", 256)
     wide = _lin(128, 640)
     rec.calls.clear()
     wide.forward(torch.zeros((2048, 128), dtype=torch.half), {})
@@ -91,17 +87,28 @@ def test_reconstruct_hgemm_sequences(monkeypatch):
     assert rec.names() == ["had_r_128"] + ["reconstruct_slice", "hgemm"] * 3 + ["had_r_128"]
 
 
-def test_weight_tensor_composition(monkeypatch):
-    """get_weight_tensor = diag(suh) H128 W_hat H128 diag(svh) (exl3.py:227-237) from the inner weights."""
-    k, n = 128, 256
-    lin = _lin(k, n)
-    rng = np.random.default_rng(0)
-    W = torch.from_numpy(rng.standard_normal((k, n)).astype(np.float16))
-    lin.suh = torch.from_numpy(rng.standard_normal(k).astype(np.float16)); lin.svh = torch.from_numpy(rng.standard_normal(n).astype(np.float16))
-    monkeypatch.setattr(ext, "reconstruct", lambda w, tr, K, mcg, mul1: w.copy_(W))
-    got = lin.get_weight_tensor().double()
-    from oracle import exl3_oracle as orc
-    H = torch.from_numpy(orc.hadamard_matrix_128() / np.sqrt(128.0))
-    want = (H @ W.double()) * lin.suh.double().unsqueeze(1)
-    want = torch.cat([want[:, i:i + 128] @ H for i in range(0, n, 128)], dim=1) * lin.svh.double().unsqueeze(0)
-    assert float((got - want).abs().max() / want.abs().max()) < 5e-3
+def test_weight_accessors_use_the_reconstruct_kernels(monkeypatch):
+    """weight_inner = decoded trellis values (reconstruct); weight = original-basis weights through the fused kernel
+    (reconstruct_had_slice with the full svh and offset 0) -- no torch-side Hadamard anywhere in the product."""
+    rec = Rec(monkeypatch)
+    lin = _lin(128, 256)
+    w = lin.weight_inner()
+    assert rec.names() == ["reconstruct"] and w.shape == (128, 256) and w.dtype == torch.half
+    rec.calls.clear()
+    lin.weight()
+    assert rec.names() == ["reconstruct_had_slice"] and rec.calls[0][1] == (128, 256) and rec.calls[0][4] == (256,) and rec.calls[0][-1] == 0
+
+
+def test_pointer_tables_validate_shapes():
+    from exllamav3_b200 import pointer_tables
+    a, b, c = _lin(128, 256), _lin(128, 256), _lin(256, 256)
+    B, su, sv = pointer_tables("cpu", [a, b])
+    assert B.tolist() == [a.trellis.data_ptr(), b.trellis.data_ptr()] and su.dtype == sv.dtype == torch.long
+    with pytest.raises(ValueError, match="identical shapes"):
+        pointer_tables("cpu", [a, c])
+
+
+def test_use_mgemm_answer_of_the_shim():
+    import inspect
+    src = inspect.getsource(ext.exl3_gemv_int8_max_k)
+    assert "return 0" in src

@@ -4,9 +4,8 @@ path (csrc/gemm_tc_i8_routed.cu, tag 212), against the CPU oracle's restatement 
 (exllamav3_ext/quant/exl3_gemm.cu:341-381) and against the verified default path (CUDA-core kernels, tag 100) on the same
 inputs.
 
-The kernel variant was written after round 1's GPU budget was spent and has NOT run on hardware: the GPU tests need
-EXL3B_TEST_UNVERIFIED=1 (tools/round2_checks.sh) and the path is only taken when forced
-(ext.set_gemm_path(ext.EXL3B_TAG_TC_I8_ROUTED)); by default routed calls run on the verified CUDA-core kernels.
+Verified on a B200 in round 2 (gpurun_out/r02_call1); routed mul1 calls at <= 4 rows take this path automatically, the tests
+also force it explicitly and compare with the CUDA-core twin (EXL3B_TAG_SIMT).
 """
 import os
 import numpy as np
@@ -14,8 +13,6 @@ import pytest
 import torch
 from oracle import exl3_oracle as orc
 
-UNVERIFIED = os.environ.get("EXL3B_TEST_UNVERIFIED", "0") == "1"
-needs_optin = pytest.mark.skipif(not UNVERIFIED, reason="routed int8 mgemm not yet verified on hardware; set EXL3B_TEST_UNVERIFIED=1")
 
 
 def test_routed_tag_is_declared_and_distinct():
@@ -44,7 +41,6 @@ def _setup(cuda, E, k, n, K, m, seed):
 
 
 @pytest.mark.gpu
-@needs_optin
 @pytest.mark.parametrize("K,m", [(4, 1), (3, 2), (6, 1), (4, 4)])
 def test_routed_i8_mgemm_moe_modes(cuda, K, m):
     from exllamav3_b200 import ext
@@ -111,7 +107,6 @@ def test_routed_i8_mgemm_moe_modes(cuda, K, m):
 
 
 @pytest.mark.gpu
-@needs_optin
 def test_routed_i8_mgemm_mixtral_shapes_properties(cuda):
     """Mixtral expert shapes (BASELINE config 5), top-2 of 8: weighted down-projection is linear in the routing weights, and
     the routed result equals the single-matrix kernel's per-expert outputs combined on the host."""
@@ -145,7 +140,6 @@ def test_routed_i8_mgemm_mixtral_shapes_properties(cuda):
 
 
 @pytest.mark.gpu
-@needs_optin
 @pytest.mark.parametrize("m,cb", [(8, 2), (32, 2), (1, 0), (17, 1)])
 def test_mgemm_split_matches_fused_default(cuda, monkeypatch, m, cb):
     """EXL3B_MGEMM_SPLIT (ext.py): dense multi-matrix calls the int8 kernel cannot take, issued as one exact tcgen05 exl3_gemm
@@ -175,7 +169,6 @@ def test_mgemm_split_matches_fused_default(cuda, monkeypatch, m, cb):
 
 
 @pytest.mark.gpu
-@needs_optin
 @pytest.mark.parametrize("m", [5, 8])
 def test_dense_mgemm_i8_eight_row_variant(cuda, m):
     """The 8-row instantiation of the int8 kernel (verified for single matrices, test_gpu_parity.py::test_gemm_i8_tensor_core_path)

@@ -3,8 +3,8 @@ Drop-in check at the Python level, run where the reference checkout exists (this
 REFERENCE'S OWN `exllamav3/modules/quant/exl3.py` (LinearEXL3) is loaded from /root/reference -- unmodified, never copied --
 with its `ext` import bound to this repo's shim (`exllamav3_b200.ext`), exactly what INTEGRATION.md's three-line patch does.
 Every call the reference module then makes into the extension is bound against the shim's real signatures (a wrong argument
-count or a missing name fails here), and the reference's dispatch is compared with this repo's mirror class on the same
-inputs.  No kernel runs: the shim's entry points are wrapped by recorders after their signatures have been checked.
+count or a missing name fails here), and the reference's dispatch is compared with this repo's own minimal caller (QLinear)
+on the same inputs: both must issue the same extension calls with the same argument shapes.  No kernel runs: the shim's entry points are wrapped by recorders after their signatures have been checked.
 """
 import importlib.util, inspect, os, sys, types
 import pytest
@@ -17,7 +17,8 @@ pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "modules", 
 
 @pytest.fixture()
 def ref_exl3(monkeypatch):
-    from exllamav3_b200 import ext, hadamard, linear_exl3
+    from exllamav3_b200 import ext
+    import refstubs
     calls = []
 
     def wrap(name):
@@ -44,14 +45,14 @@ def ref_exl3(monkeypatch):
     class Config: pass
     mod("exllamav3")
     mod("exllamav3.model")
-    mod("exllamav3.model.config", Config=Config, NullConfig=linear_exl3.NullConfig)
+    mod("exllamav3.model.config", Config=Config, NullConfig=refstubs.NullConfig)
     mod("exllamav3.ext", exllamav3_ext=ext)                       # <- INTEGRATION.md: the extension module IS the shim
     mod("exllamav3.util", profile_opt=lambda f: f)
-    mod("exllamav3.util.tensor", g_tensor_cache=linear_exl3.g_tensor_cache)
+    mod("exllamav3.util.tensor", g_tensor_cache=refstubs.g_tensor_cache)
     mod("exllamav3.modules")
     mod("exllamav3.modules.quant")
     mod("exllamav3.modules.quant.exl3_lib")
-    mod("exllamav3.modules.quant.exl3_lib.quantize", preapply_had_l=hadamard.preapply_had_l, preapply_had_r=hadamard.preapply_had_r,
+    mod("exllamav3.modules.quant.exl3_lib.quantize", preapply_had_l=refstubs.preapply_had_l, preapply_had_r=refstubs.preapply_had_r,
         had_k=128, had_n=128)
     spec = importlib.util.spec_from_file_location("exllamav3.modules.quant.exl3", os.path.join(REF, "modules", "quant", "exl3.py"))
     m = importlib.util.module_from_spec(spec)
@@ -66,13 +67,19 @@ def _tensors(k, n, K=4):
     return dict(suh=torch.ones(k, dtype=torch.half), svh=torch.ones(n, dtype=torch.half), trellis=tr, mul1=torch.zeros((), dtype=torch.int))
 
 
+def _qlin(t, **kw):
+    from exllamav3_b200 import QLinear
+    return QLinear(t["trellis"], t["suh"], t["svh"], mul1=True, **kw)
+
+
 def test_reference_linear_exl3_runs_on_the_shim_and_matches_the_mirror(ref_exl3):
     ref_mod, calls = ref_exl3
-    from exllamav3_b200 import LinearEXL3 as Mirror
-    assert ref_mod.AUTO_RECONSTRUCT_THRESHOLD == 144 and ref_mod.MAX_RECONSTRUCT_SLICE_N == 32768
+    from exllamav3_b200 import qlinear
+    assert ref_mod.AUTO_RECONSTRUCT_THRESHOLD == qlinear.KERNEL_MAX_ROWS == 144
+    assert ref_mod.MAX_RECONSTRUCT_SLICE_N == qlinear.DENSE_WINDOW_COLS == 32768
     k, n = 256, 384
     ref_lin = ref_mod.LinearEXL3(None, k, n, key="q", **_tensors(k, n))          # constructs ext.BC_LinearEXL3 from the shim
-    mir_lin = Mirror(None, k, n, key="q", **_tensors(k, n))
+    mir_lin = _qlin(_tensors(k, n))
     from exllamav3_b200 import ext
     assert isinstance(ref_lin.bc, ext.BC_LinearEXL3) and ref_lin.K == 4 and ref_lin.mul1 and not ref_lin.mcg
     for (shape, params, out_dtype) in (((1, k), {}, None), ((144, k), {}, torch.float), ((3, 7, k), {}, None),
@@ -89,11 +96,11 @@ def test_reference_linear_exl3_runs_on_the_shim_and_matches_the_mirror(ref_exl3)
 
 def test_reference_wide_output_slicing_matches_the_mirror(ref_exl3, monkeypatch):
     ref_mod, calls = ref_exl3
-    from exllamav3_b200 import LinearEXL3 as Mirror, linear_exl3
+    from exllamav3_b200 import qlinear
     monkeypatch.setattr(ref_mod, "MAX_RECONSTRUCT_SLICE_N", 256)
-    monkeypatch.setattr(linear_exl3, "MAX_RECONSTRUCT_SLICE_N", 256)
+    monkeypatch.setattr(qlinear, "DENSE_WINDOW_COLS", 256)
     k, n = 128, 640
-    ref_lin = ref_mod.LinearEXL3(None, k, n, **_tensors(k, n)); mir_lin = Mirror(None, k, n, **_tensors(k, n))
+    ref_lin = ref_mod.LinearEXL3(None, k, n, **_tensors(k, n)); mir_lin = _qlin(_tensors(k, n))
     for rows in (200, 2048):
         x = torch.zeros((rows, k), dtype=torch.half)
         calls.clear(); ref_lin.forward(x, {}); a = list(calls)
@@ -102,23 +109,25 @@ def test_reference_wide_output_slicing_matches_the_mirror(ref_exl3, monkeypatch)
 
 
 def test_reference_multilinear_tables_match_the_mirror():
-    """modules/multilinear.py builds the pointer tables exl3_mgemm reads; the mirror must build the same ones."""
+    """modules/multilinear.py builds the pointer tables exl3_mgemm reads; pointer_tables must build the same ones."""
     src = open(os.path.join(REF, "modules", "multilinear.py")).read()
     ns = {}
     exec(compile(src.replace("from . import Linear", "Linear = object"), "multilinear_ref", "exec"), ns)     # executed in memory, not copied
-    from exllamav3_b200 import LinearEXL3 as Mirror, MultiLinear
+    from exllamav3_b200 import pointer_tables
     k, n = 128, 256
-    inners = [Mirror(None, k, n, **_tensors(k, n)) for _ in range(3)]
+    inners = [_qlin(_tensors(k, n)) for _ in range(3)]
+    for i in inners:
+        i.quant_type = "exl3"                                   # the attribute the reference's table builder asserts on
 
     class Lin:                                                  # the reference wraps LinearEXL3 in modules.Linear (.inner)
         def __init__(self, inner):
             self.inner, self.quant_type, self.softcap, self.post_scale = inner, "exl3", 0.0, 1.0
             self.in_features, self.out_features = inner.in_features, inner.out_features
     ref_ml = ns["MultiLinear"]("cpu", [Lin(i) for i in inners])
-    ml = MultiLinear("cpu", inners)
+    ml = dict(zip(("ptrs_trellis", "ptrs_suh", "ptrs_svh"), pointer_tables("cpu", inners)))
     for a in ("ptrs_trellis", "ptrs_suh", "ptrs_svh"):
-        assert torch.equal(getattr(ref_ml, a), getattr(ml, a)) and getattr(ml, a).dtype == torch.long
-    assert (ref_ml.K, ref_ml.mcg, ref_ml.mul1, ref_ml.in_features, ref_ml.out_features) == (ml.K, ml.mcg, ml.mul1, ml.in_features, ml.out_features)
+        assert torch.equal(getattr(ref_ml, a), ml[a]) and ml[a].dtype == torch.long
+    assert (ref_ml.K, ref_ml.mcg, ref_ml.mul1, ref_ml.in_features, ref_ml.out_features) == (4, False, True, k, n)
 
 
 def test_every_reference_call_site_of_the_qgemm_surface_fits_the_shim():
@@ -199,9 +208,9 @@ def test_reference_use_mgemm_policy_with_the_shims_answer(monkeypatch):
 
 def test_reference_tp_import_split_equals_tp_slice(ref_exl3):
     """The reference's OWN shard construction (LinearEXL3.tp_export / tp_import_split, modules/quant/exl3.py:268-330), run with a
-    trivial in-process stand-in for its SHM producer / consumer transport, against this repo's LinearEXL3.tp_slice."""
+    trivial in-process stand-in for its SHM producer / consumer transport, against this repo's tp.tp_slice."""
     ref_mod, _ = ref_exl3
-    from exllamav3_b200 import LinearEXL3 as Mirror, tp
+    from exllamav3_b200 import tp
 
     class Producer:
         def send(self, t): return t
@@ -218,14 +227,14 @@ def test_reference_tp_import_split_equals_tp_slice(ref_exl3):
     tens["suh"] = torch.randn(k, generator=g).half(); tens["svh"] = torch.randn(n, generator=g).half()
     bias = torch.randn(n, generator=g).half()
     ref_full = ref_mod.LinearEXL3(None, k, n, bias=bias, out_dtype=torch.float, **tens)
-    mir_full = Mirror(None, k, n, bias=bias, out_dtype=torch.float, **tens)
+    mir_full = _qlin(tens, bias=bias, out_dtype=torch.float)
     exported = ref_full.tp_export(None, Producer())
     ctx = {"consumer": Consumer(), "device": "cpu"}
     world = 3
     splits = [(True, a, b) for (a, b) in tp.split_ranges(n, world)] + [(False, a, b) for (a, b) in tp.split_ranges(k, world)] + [None]
     for split in splits:
         r = ref_mod.LinearEXL3.tp_import_split(ctx, exported, None, split)
-        m = mir_full.tp_slice(split)
+        m = tp.tp_slice(mir_full, split)
         assert (r.in_features, r.out_features, r.K, r.mcg, r.mul1, r.out_dtype) == (m.in_features, m.out_features, m.K, m.mcg, m.mul1, m.out_dtype)
         assert torch.equal(r.trellis, m.trellis) and torch.equal(r.suh, m.suh) and torch.equal(r.svh, m.svh)
         assert (r.bias is None) == (m.bias is None) and (r.bias is None or torch.equal(r.bias, m.bias))

@@ -3,10 +3,9 @@ Row-parallel GEMM with the tensor-parallel sum fused into its epilogue (csrc/gem
 
 CPU part (always runs): eligibility rules, argument validation, the host-side selection in tp.row_parallel_forward.
 
-GPU part: the kernel was written after round 1's GPU budget was spent, so it has NOT run on hardware yet.  Its tests are
-real parity tests (loop-back protocol test on one GPU, two-process test on two GPUs) but they only run with
-EXL3B_TEST_UNVERIFIED=1, so that an unverified kernel cannot turn the verified suite red; tools/round2_checks.sh runs them
-first thing in round 2.
+GPU part (verified on a B200 in round 2, gpurun_out/r02_call1): world-1 equality with the plain kernel and the loop-back
+protocol test run on one GPU (-m gpu); the two-process test needs two GPUs and carries the `multigpu` marker instead
+(gpurun --gpus 2 -- python -m pytest tests -m multigpu).
 """
 import ctypes, os
 import numpy as np
@@ -14,8 +13,6 @@ import pytest
 import torch
 from oracle import exl3_oracle as orc
 
-UNVERIFIED = os.environ.get("EXL3B_TEST_UNVERIFIED", "0") == "1"
-needs_optin = pytest.mark.skipif(not UNVERIFIED, reason="fused all-reduce kernel not yet verified on hardware; set EXL3B_TEST_UNVERIFIED=1")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -58,13 +55,13 @@ def test_tp_setup_validation_without_gpu():
 
 def test_row_parallel_forward_selection_host_logic():
     """tp.row_parallel_forward takes the one-kernel path only when enabled and eligible (mul1, <= 4 rows, no bias)."""
-    from exllamav3_b200 import tp, LinearEXL3
+    from exllamav3_b200 import tp, QLinear
     k, n, K = 256, 384, 4
     tr, suh, svh, _ = orc.make_synthetic(k, n, K)
-    mk = lambda **kw: LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr), **kw)
-    mul1 = mk(mul1=torch.zeros((), dtype=torch.int))
+    mk = lambda **kw: QLinear(torch.from_numpy(tr), torch.from_numpy(suh), torch.from_numpy(svh), **kw)
+    mul1 = mk(mul1=True)
     three = mk()
-    biased = mk(mul1=torch.zeros((), dtype=torch.int), bias=torch.zeros(n, dtype=torch.half))
+    biased = mk(mul1=True, bias=torch.zeros(n, dtype=torch.half))
     assert not tp.fused_allreduce_eligible(mul1, 1)                       # not enabled
     saved = dict(tp._fused)
     try:
@@ -73,6 +70,12 @@ def test_row_parallel_forward_selection_host_logic():
         assert not tp.fused_allreduce_eligible(mul1, 5)                   # rows
         assert not tp.fused_allreduce_eligible(three, 1)                  # codebook
         assert not tp.fused_allreduce_eligible(biased, 1)                 # bias on this shard
+        # rank invariance: the row shard that does NOT hold the bias (first != 0) must give the same answer as the one that does
+        s0, s1 = tp.tp_slice(biased, (False, 0, 128)), tp.tp_slice(biased, (False, 128, 256))
+        assert s0.bias is not None and s1.bias is None and s0.bias_in_group and s1.bias_in_group
+        assert not tp.fused_allreduce_eligible(s0, 1) and not tp.fused_allreduce_eligible(s1, 1)
+        u0, u1 = tp.tp_slice(mul1, (False, 0, 128)), tp.tp_slice(mul1, (False, 128, 256))
+        assert tp.fused_allreduce_eligible(u0, 1) and tp.fused_allreduce_eligible(u1, 1)
         assert not tp.fused_allreduce_eligible(mul1, 1, any_bias=True)    # bias on some other rank's shard
         tp._fused.update(max_elems=384)
         assert tp.fused_allreduce_eligible(mul1, 1) and not tp.fused_allreduce_eligible(mul1, 2)   # slot size
@@ -98,7 +101,6 @@ def _plain_gemm(ext, dev, x, tr, suh, svh, K, fp32=True):
 
 
 @pytest.mark.gpu
-@needs_optin
 @pytest.mark.parametrize("K,m", [(4, 1), (4, 4), (2, 3), (6, 1)])
 def test_fused_allreduce_world1_equals_plain_gemm(cuda, K, m):
     """world = 1: no peers; the fused kernel must reproduce exl3_gemm bit for bit (fp32 C) and advance the epoch."""
@@ -122,7 +124,6 @@ def test_fused_allreduce_world1_equals_plain_gemm(cuda, K, m):
 
 
 @pytest.mark.gpu
-@needs_optin
 @pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (4, 2), (8, 7)])
 def test_fused_allreduce_loopback_protocol(cuda, world, rank):
     """
@@ -179,11 +180,10 @@ def _two_rank_worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        from exllamav3_b200 import ext, tp, LinearEXL3
+        from exllamav3_b200 import ext, tp, QLinear
         K, m, k_full, n = 4, 1, 4096, 4096
         tr, suh, svh, x = orc.make_synthetic(k_full, n, K, m=m)
-        lin = LinearEXL3(None, k_full, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr),
-                         mul1=torch.zeros((), dtype=torch.int), out_dtype=torch.float)
+        lin = QLinear(torch.from_numpy(tr), torch.from_numpy(suh), torch.from_numpy(svh), mul1=True, out_dtype=torch.float)
         shard = tp.row_shard(lin, rank, world, dev)
         first, last = tp.split_ranges(k_full, world)[rank]
         xl = torch.from_numpy(np.ascontiguousarray(x[:, first:last])).to(dev)
@@ -206,8 +206,7 @@ def _two_rank_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.gpu
-@needs_optin
+@pytest.mark.multigpu
 def test_fused_allreduce_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -19,12 +19,11 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from exllamav3_b200 import LinearEXL3, tp
+        from exllamav3_b200 import QLinear, tp
         from oracle import exl3_oracle as orc
         k, n, K, cb, m = 512, 768, 4, 2, 3
         tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
-        lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr),
-                         mul1=torch.zeros((), dtype=torch.int))
+        lin = QLinear(torch.from_numpy(tr), torch.from_numpy(suh), torch.from_numpy(svh), mul1=True)
         full = orc.exl3_gemm_f64(x, tr, suh, svh, K, cb)
 
         def local_gemm(shard, x_local):       # oracle stands in for the CUDA kernel on this GPU-less box
@@ -66,12 +65,11 @@ def _worker_rank_ordered(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from exllamav3_b200 import LinearEXL3, tp
+        from exllamav3_b200 import QLinear, tp
         from oracle import exl3_oracle as orc
         k, n, K, cb, m = 768, 512, 4, 2, 2
         tr, suh, svh, x = orc.make_synthetic(k, n, K, m=m)
-        lin = LinearEXL3(None, k, n, suh=torch.from_numpy(suh), svh=torch.from_numpy(svh), trellis=torch.from_numpy(tr),
-                         mul1=torch.zeros((), dtype=torch.int))
+        lin = QLinear(torch.from_numpy(tr), torch.from_numpy(suh), torch.from_numpy(svh), mul1=True)
         rs = tp.row_shard(lin, rank, world)
         first, last = tp.split_ranges(k, world)[rank]
         part = torch.from_numpy(orc.exl3_gemm_f64(np.ascontiguousarray(x[:, first:last]), rs.trellis.numpy(), rs.suh.numpy(),

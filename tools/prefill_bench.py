@@ -3,7 +3,7 @@ and of the fused decode-GEMM kernel at mid m.  python tools/prefill_bench.py"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from exllamav3_b200 import ext, LinearEXL3
+from exllamav3_b200 import ext, QLinear
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(0)
 peak = 1673.7
@@ -14,7 +14,7 @@ except Exception:
 for (k, n, K) in ((4096, 4096, 4), (4096, 14336, 4), (14336, 4096, 4)):
     tr = torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
     suh = (torch.randn(k, generator=g, device=dev) / k ** 0.5).half(); svh = torch.randn(n, generator=g, device=dev).half()
-    lin = LinearEXL3(None, k, n, suh=suh, svh=svh, trellis=tr, mul1=torch.zeros((), dtype=torch.int, device=dev))
+    lin = QLinear(tr, suh, svh, mul1=True)
     for m in (16, 64, 128, 256, 1024, 2048, 8192, 65536):
         if m * max(k, n) * 2 > 6e9:
             continue
