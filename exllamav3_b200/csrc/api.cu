@@ -62,6 +62,10 @@ int get_ctx(DevCtx** out)
         c.xh_tiled_slot_bytes = (size_t) 2 * 256 * DevCtx::XH_MAX_K;
         EXL3B_CUDA(cudaMalloc(&c.xh_tiled, c.xh_tiled_slot_bytes * DevCtx::XH_SLOTS));
         EXL3B_CUDA(cudaMemset(c.xh_tiled, 0, c.xh_tiled_slot_bytes * DevCtx::XH_SLOTS));
+        EXL3B_CUDA(cudaMalloc(&c.chain_ctr, 256 * sizeof(unsigned int)));
+        EXL3B_CUDA(cudaMemset(c.chain_ctr, 0, 256 * sizeof(unsigned int)));
+        EXL3B_CUDA(cudaMalloc(&c.chain_parts, (size_t) 2 * DevCtx::I8_PART_CTAS * 512 * sizeof(float)));
+        EXL3B_CUDA(cudaMemset(c.chain_parts, 0xff, (size_t) 2 * DevCtx::I8_PART_CTAS * 512 * sizeof(float)));
         c.xh_scratch_elems = (size_t) 256 * DevCtx::XH_MAX_K;
         EXL3B_CUDA(cudaMalloc(&c.xh_scratch, c.xh_scratch_elems * sizeof(half)));
         EXL3B_CUDA(cudaDeviceSynchronize());
@@ -191,6 +195,11 @@ static int select_gemm_path(const GemmArgs& g, int force_shape_idx = -1)
         EXL3B_CHECK(force_shape_idx <= 2, EXL3B_ERR_ARG, "exl3_gemm: force_shape_idx %d out of range (1 = CUDA-core, 2 = tcgen05)", force_shape_idx);
         path = force_shape_idx == 1 ? EXL3B_TAG_SIMT : EXL3B_TAG_TC;
     }
+    if (path == EXL3B_TAG_TC_I8_CHAIN)
+    {
+        EXL3B_CHECK(gemm_chain_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: chain kernel forced but unsupported (needs mul1, m <= 4)");
+        return EXL3B_TAG_TC_I8_CHAIN;
+    }
     if (path == EXL3B_TAG_TC_I8)
         EXL3B_CHECK(gemm_tc_i8_supported(g), EXL3B_ERR_UNSUPPORTED, "exl3_gemm: int8 tensor-core path forced but unsupported (needs mul1, m <= 4, or m <= 8 with m * k <= 32768)");
     if (path == EXL3B_TAG_TC)
@@ -259,6 +268,7 @@ int exl3b_gemm(void* stream_, const void* A, const void* B, void* C, const void*
 
     int path = select_gemm_path(g, force_shape_idx);
     if (path < 0) return path;
+    if (path == EXL3B_TAG_TC_I8_CHAIN) return launch_gemm_chain(stream, ctx, g);
     if (path == EXL3B_TAG_TC_I8) return launch_gemm_tc_i8(stream, ctx, g);
     if (path == EXL3B_TAG_TC) return launch_gemm_tc(stream, ctx, g);
     return launch_gemm_simt(stream, ctx, g);
@@ -347,6 +357,27 @@ int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, co
         return launch_mgemm_tc_i8_routed((cudaStream_t) stream, ctx, a);
     return launch_mgemm((cudaStream_t) stream, ctx, a);
 }
+
+int exl3b_chain_plan(const struct exl3b_chain_op* ops, int n_ops, int num_sms, struct exl3b_chain_plan* out)
+{
+    EXL3B_CHECK(out && num_sms >= 1, EXL3B_ERR_ARG, "exl3_chain_plan: bad argument");
+    return chain_plan(ops, n_ops, num_sms, out);
+}
+
+int exl3b_chain_walk(const struct exl3b_chain_op* ops, int n_ops, int num_sms, int cta, int32_t* out, int max_units)
+{
+    return chain_walk(ops, n_ops, num_sms, cta, out, max_units);
+}
+
+int exl3b_chain_create(const struct exl3b_chain_op* ops, int n_ops, void** chain)
+{
+    DevCtx* ctx; int r = get_ctx(&ctx); if (r) return r;
+    return chain_create(ctx, ops, n_ops, chain);
+}
+
+int exl3b_chain_run(void* stream, void* chain) { return chain_run((cudaStream_t) stream, chain); }
+
+int exl3b_chain_destroy(void* chain) { return chain_destroy(chain); }
 
 int exl3b_hgemm(void* stream, const void* a, const void* b, void* c, int m, int k, int n, int c_fp32,
                 int64_t c_stride)

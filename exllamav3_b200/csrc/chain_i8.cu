@@ -1,0 +1,965 @@
+// Persistent multi-GEMM decode kernel for the mul1 codebook at <= 4 rows ("chain", tag 220): ONE launch runs a list of EXL3
+// GEMMs -- a single exl3_gemm, the same-input projections of a block (q + k + v, gate + up), or a whole dependent block
+// (gate + up -> silu * mul -> down: what the reference's BC_GatedMLP issues as three launches, libtorch/mlp.cpp:14-91; the
+// projections of BC_Attention, libtorch/attention.cpp:286-365) -- with the weight stream never stopping at a GEMM boundary.
+//
+// Arithmetic per weight is that of gemm_tc_i8_body.cuh (the product word state * 0x83DCD12D written to TMEM as four u8
+// K-elements of a tcgen05.mma.kind::i8 operand, activations as balanced 16-bit integers in two int8 digits); what is new:
+//
+//   * ops and stages.  The list is cut into STAGES; the ops of a stage are independent (same or external inputs) and
+//     their 128 x 128 units form one stream-K unit space over the persistent grid; a stage's inputs may be outputs of
+//     earlier stages.  Between stages there is a grid-wide dependency: every finished 128-column output segment bumps
+//     a global counter, and only the warps that PREPARE activations wait for it.  The TMA producer and the decode warps
+//     run on into the next stage's weights (they depend on no activation), so HBM streams through the boundary and the
+//     first operand stages of the next GEMM are decoded before its input exists.
+//   * quads issue their own MMAs.  The 16 decode warps are 4 quads (one warp per TMEM lane quarter).  A quad owns
+//     every 4th unit, decodes it in four rounds of two k-tiles (32 TMEM columns) into its private ring of three operand
+//     slots, and its lead warp issues the round's four MMAs into the quad's private accumulator as soon as the quad's
+//     slot barrier completes: no central MMA warp whose wake-up / issue / commit loop paces all units, four independent
+//     short pipelines instead of two long ones.  Integer accumulation is exact and order-free, so the epilogue just adds
+//     the quads' accumulators.
+//   * activation scale without a Hadamard pass.  The quantisation scale only needs an upper bound of max |xh| over
+//     the row; xh is a block-orthonormal transform of x * suh, so max_kb || (x * suh)_kb ||_2 is one -- a plain
+//     reduction pass over the row by three warps (which also applies silu * mul for the gated-MLP input and caches
+//     x * suh in shared memory) replaces the 18-warp Hadamard prologue every CTA of the single-GEMM kernel runs.
+//     The 128-point Hadamard itself is done per unit by the digit warps from the cache, off the critical path.
+//     (|q| <= 32512 still holds; the scale is up to ~3x larger than the exact maximum, i.e. activations carry ~14.5
+//     instead of 16 bits: rel-RMS contribution 1e-4, tolerance tests in tests/test_chain.py.)
+//
+// Roles (768 threads): warp 0 TMA producer, warps 1-3 activation / digit warps, warps 4-19 decode quads, warps 20-23
+// epilogue.  TMEM: 12 operand slots x 32 columns + 8 accumulators x 16 columns = 512.
+#include "tc_common.cuh"
+#include "i8_math.cuh"
+#include <mutex>
+#include <vector>
+
+namespace exl3b {
+
+using namespace ptx;
+
+constexpr int CH_THREADS = 768;
+constexpr int CH_XF_WARP0 = 1, CH_XF_WARPS = 3;
+constexpr int CH_DEC_WARP0 = 4;
+constexpr int CH_QUADS = 4, CH_SLOTS = 3, CH_SLOT_COLS = 32;
+constexpr int CH_EPI_WARP0 = 20;
+constexpr int CH_D_COL0 = CH_QUADS * CH_SLOTS * CH_SLOT_COLS;          // 384
+constexpr int CH_NT = 16, CH_MR = 4;
+constexpr int CH_B_BYTES = 4096, CH_B_STAGE = 4096 + 64;               // digit tile + per-row digit sums
+constexpr int CH_SUB_UNITS = 96;                                       // int32 accumulator safety (see I8_SUB_UNITS)
+constexpr int CH_MAX_STAGES = 16;
+constexpr int CH_MAX_INLINE = 4;
+constexpr int CH_SCALE_SLOTS = 32;
+constexpr uint32_t CH_SENTINEL = 0xffffffffu;
+constexpr int CH_CACHE_MAX = 64 * 1024;
+
+struct ChainOp
+{
+    const void* A;            // in_mode 0: fp16 (m, k); 1: gate, fp32 (m, k); 2: gate, fp16 (m, k)
+    const void* A2;           // in_mode 1 / 2: up, same dtype
+    const half* suh; const half* svh;
+    void* C;
+    int m, k, n, K;
+    int c_fp32, in_mode;
+    int KB, strips;
+    int stage;
+    int cached;               // x * suh kept in shared memory (m * k * 2 <= cache bytes)
+    long long unit_off;       // first unit of this op in its stage's unit space
+    float out_scale;
+    int pad_;
+};
+
+struct ChainStage { int op_begin, op_end; int strips_total; int pad_; long long U; };
+
+struct ChainParams
+{
+    const ChainOp* ops; const ChainStage* stages; const CUtensorMap* tmaps;     // device tables (n_inline == 0)
+    int n_ops, n_stages, n_inline;
+    int S, w_bytes, cache_bytes;
+    unsigned int* ctr;        // [n_stages] finished output segments per stage, [n_stages] exit ticket; zero between launches
+    float* parts;             // split-K exchange, [2][grid][MR * 128] words, sentinel between launches
+    unsigned long long* dbg;
+    ChainOp ops_inline[CH_MAX_INLINE];
+    ChainStage stages_inline[CH_MAX_INLINE];
+    CUtensorMap tmaps_inline[CH_MAX_INLINE];
+};
+
+struct ChainSmem { int off_b, off_tile, off_bars, off_cache, total; };
+
+__host__ __device__ inline ChainSmem chain_smem(int S, int w_bytes, int cache_bytes)
+{
+    ChainSmem L;
+    L.off_b = S * w_bytes;
+    L.off_tile = L.off_b + S * CH_B_STAGE;
+    L.off_tile = (L.off_tile + 127) & ~127;
+    L.off_bars = L.off_tile + CH_MR * 128 * 4;
+    L.off_cache = L.off_bars + 2048;
+    L.total = L.off_cache + cache_bytes;
+    return L;
+}
+
+// ---- the CTA's walk over its units: stage by stage, inside a stage op by op, strip by strip, k fastest ------------------
+struct Cursor
+{
+    const ChainOp* ops; const ChainStage* stages;
+    int n_stages, cta, G;
+    int stage, op, strip, kb, KB, strips;
+    long long u, uend;
+    int seq;                  // running index of the unit on this CTA over the whole chain: ring stage, quad, digit warp
+    int run_begin, run_end;   // [seq range) of the CTA's units inside the current (op, strip)
+    bool valid;
+
+    __host__ __device__ __forceinline__ void start_run()
+    {
+        const long long left_cta = uend - u;
+        const int left_strip = KB - kb;
+        run_begin = seq;
+        run_end = seq + (int) (left_cta < left_strip ? left_cta : left_strip);
+    }
+    __host__ __device__ __forceinline__ void enter_stage()
+    {
+        valid = false;
+        while (++stage < n_stages)
+        {
+            const long long U = stages[stage].U;
+            const long long ub = unit_begin(U, G, cta), ue = unit_begin(U, G, cta + 1);
+            if (ue <= ub) continue;
+            u = ub; uend = ue;
+            op = stages[stage].op_begin;
+            while (u >= ops[op].unit_off + (long long) ops[op].KB * ops[op].strips) ++op;
+            KB = ops[op].KB; strips = ops[op].strips;
+            const long long rel = u - ops[op].unit_off;
+            strip = (int) (rel / KB); kb = (int) (rel - (long long) strip * KB);
+            start_run();
+            valid = true;
+            return;
+        }
+    }
+    __host__ __device__ __forceinline__ void init(const ChainOp* o, const ChainStage* s, int ns, int cta_, int G_)
+    {
+        ops = o; stages = s; n_stages = ns; cta = cta_; G = G_;
+        stage = -1; seq = 0;
+        enter_stage();
+    }
+    __host__ __device__ __forceinline__ void next()
+    {
+        ++seq; ++u;
+        if (u == uend) { enter_stage(); return; }
+        if (++kb == KB)
+        {
+            kb = 0;
+            if (++strip == strips) { strip = 0; ++op; KB = ops[op].KB; strips = ops[op].strips; }
+            start_run();
+        }
+    }
+    // bounds of the accumulation chunk (<= CH_SUB_UNITS units of the run) that holds the current unit
+    __host__ __device__ __forceinline__ void sub_bounds(int& sb, int& se) const
+    {
+        sb = run_begin + (seq - run_begin) / CH_SUB_UNITS * CH_SUB_UNITS;
+        se = sb + CH_SUB_UNITS < run_end ? sb + CH_SUB_UNITS : run_end;
+    }
+};
+
+template <int K>
+__device__ __forceinline__ void ch_load_tiles2(const uint32_t* wst, int tl, int chunk, int prev_lane, int t0, uint32_t (&w)[2][K + 1])
+{
+    #pragma unroll
+    for (int j = 0; j < 2; ++j)
+    {
+        const uint32_t* cp = wst + ((t0 + j) * 8 + tl) * (8 * K) + chunk * K;
+        if constexpr (K % 4 == 0)
+        {
+            #pragma unroll
+            for (int i = 0; i < K; i += 4)
+            {
+                uint4 v = *reinterpret_cast<const uint4*>(cp + i);
+                w[j][1 + i] = v.x; w[j][2 + i] = v.y; w[j][3 + i] = v.z; w[j][4 + i] = v.w;
+            }
+        }
+        else if constexpr (K % 2 == 0)
+        {
+            #pragma unroll
+            for (int i = 0; i < K; i += 2)
+            {
+                uint2 v = *reinterpret_cast<const uint2*>(cp + i);
+                w[j][1 + i] = v.x; w[j][2 + i] = v.y;
+            }
+        }
+        else
+        {
+            #pragma unroll
+            for (int i = 0; i < K; ++i) w[j][1 + i] = cp[i];
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 2; ++j)
+        w[j][0] = __shfl_sync(0xffffffffu, w[j][K], prev_lane);
+}
+
+__device__ __forceinline__ float silu_f32(float x) { return x * __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Shared state of a decode quad's warp across its units
+struct QuadState
+{
+    int slot, slph;           // operand-slot ring of the quad (one step per round)
+    int dbuf, dph;            // accumulator buffer of the quad (one step per accumulation chunk)
+    uint32_t acc;             // accumulate flag of the next MMA
+    int tsum;                 // lane r < m of the lead warp: digit sum of row r over the chunk so far
+};
+
+struct ChainCtx
+{
+    uint8_t* smem;
+    uint32_t bar0;
+    int S, w_bytes;
+    ChainSmem L;
+    uint32_t tmem_base;
+    __device__ __forceinline__ uint32_t W_FULL(int s) const { return bar0 + 8u * s; }
+    __device__ __forceinline__ uint32_t W_EMPTY(int s) const { return bar0 + 8u * (CH_MAX_STAGES + s); }
+    __device__ __forceinline__ uint32_t X_FULL(int s) const { return bar0 + 8u * (2 * CH_MAX_STAGES + s); }
+    __device__ __forceinline__ uint32_t SLOT_FULL(int Q, int sl) const { return bar0 + 8u * (3 * CH_MAX_STAGES + Q * CH_SLOTS + sl); }
+    __device__ __forceinline__ uint32_t SLOT_EMPTY(int Q, int sl) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 12 + Q * CH_SLOTS + sl); }
+    __device__ __forceinline__ uint32_t D_FULL(int Q, int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 24 + Q * 2 + b); }
+    __device__ __forceinline__ uint32_t D_EMPTY(int Q, int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 32 + Q * 2 + b); }
+};
+constexpr int CH_NUM_BARS = 3 * CH_MAX_STAGES + 40;                    // 88 barriers = 704 B
+
+// One unit (128 k x 128 n weights) of a decode quad: four rounds of two k-tiles.
+template <int K>
+__device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int Q, int q, int lane, int s, int wph,
+                                          bool first, bool last, int m, int* s_tout)
+{
+    const int tl = strip_tile(q, lane), chunk = lane & 7;
+    const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
+    const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+    const bool lead = q == 0;
+    mbar_wait<32>(cx.W_FULL(s), wph);
+    const uint32_t* wst = reinterpret_cast<const uint32_t*>(cx.smem + s * cx.w_bytes);
+    const uint32_t idesc = idesc_u8s8_s32(128, CH_NT);
+    const uint32_t x_smem = smem_u32(cx.smem + cx.L.off_b + s * CH_B_STAGE);
+    const uint64_t desc0 = smem_desc(x_smem, 128, 4096, 0);
+    const uint32_t desc_hi = (uint32_t) (desc0 >> 32);
+    uint32_t desc_lo = (uint32_t) desc0;
+    int tload = 0;
+    #pragma unroll 1
+    for (int tp = 0; tp < 4; ++tp)
+    {
+        uint32_t w[2][K + 1];
+        ch_load_tiles2<K>(wst, tl, chunk, prev_lane, 2 * tp, w);
+        mbar_wait(cx.SLOT_EMPTY(Q, qs.slot), qs.slph ^ 1);
+        tc_fence_after();
+        const uint32_t a_col = (uint32_t) ((Q * CH_SLOTS + qs.slot) * CH_SLOT_COLS);
+        #pragma unroll
+        for (int j = 0; j < 2; ++j)
+        {
+            uint32_t o[16];
+            if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
+            tmem_st_32x32b_x16(cx.tmem_base + lane_base + a_col + 16 * j, o);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+        {
+            mbar_arrive(cx.SLOT_FULL(Q, qs.slot));
+            if (tp == 3) mbar_arrive(cx.W_EMPTY(s));
+        }
+        if (lead)
+        {
+            if (tp == 0)
+            {
+                mbar_wait(cx.X_FULL(s), wph);                         // this unit's activation digits are in place
+                if (first)
+                {
+                    mbar_wait(cx.D_EMPTY(Q, qs.dbuf), qs.dph ^ 1);    // the epilogue has drained this accumulator
+                    qs.acc = 0; qs.tsum = 0;
+                }
+                if (lane < m) tload = *reinterpret_cast<const int*>(cx.smem + cx.L.off_b + s * CH_B_STAGE + CH_B_BYTES + 4 * lane);
+                qs.tsum += tload;
+            }
+            mbar_wait(cx.SLOT_FULL(Q, qs.slot), qs.slph);
+            tc_fence_after();
+            const bool fin = tp == 3 && last;
+            if (fin)
+            {
+                if (lane < m) s_tout[(Q * 2 + qs.dbuf) * CH_MR + lane] = qs.tsum;     // visible to the epilogue before D_FULL fires
+                __threadfence_block();
+                __syncwarp();
+            }
+            if (elect_one())
+            {
+                const uint32_t d_addr = cx.tmem_base + CH_D_COL0 + (Q * 2 + qs.dbuf) * CH_NT;
+                uint32_t a_addr = cx.tmem_base + a_col;
+                uint32_t dl = desc_lo;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    mma_i8_ts_step<8, 16>(d_addr, a_addr, dl, desc_hi, idesc, qs.acc);
+                    qs.acc = 1;
+                }
+                tc_commit(cx.SLOT_EMPTY(Q, qs.slot));
+                if (tp == 3) tc_commit(cx.W_EMPTY(s));
+                if (fin) tc_commit(cx.D_FULL(Q, qs.dbuf));
+            }
+            qs.acc = 1;
+            __syncwarp();
+            desc_lo += 64;
+            if (fin) { qs.dbuf ^= 1; if (qs.dbuf == 0) qs.dph ^= 1; }
+        }
+        if (++qs.slot == CH_SLOTS) { qs.slot = 0; qs.slph ^= 1; }
+    }
+}
+
+__device__ __forceinline__ void ch_watchdog(uint32_t& polls, unsigned long long& t0, const char* what, int a, int b)
+{
+    if ((++polls & 255u) == 0)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) { printf("exl3b chain: %s timeout (block %d, %d, %d)\n", what, blockIdx.x, a, b); __trap(); }
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chain_i8_kernel(const __grid_constant__ ChainParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ChainOp* ops = p.n_inline ? p.ops_inline : p.ops;
+    const ChainStage* stages = p.n_inline ? p.stages_inline : p.stages;
+    const CUtensorMap* tmaps = p.n_inline ? p.tmaps_inline : p.tmaps;
+    const int S = p.S;
+    ChainCtx cx;
+    cx.smem = smem; cx.S = S; cx.w_bytes = p.w_bytes; cx.L = chain_smem(S, p.w_bytes, p.cache_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cx.L.off_bars);
+    cx.bar0 = smem_u32(bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cx.L.off_bars + 8 * CH_NUM_BARS);              // +704
+    unsigned int* s_norm2 = reinterpret_cast<unsigned int*>(tmem_slot + 4);                                  // [MR] float bits
+    int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                                                     // [4][2][MR]
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 8 + 32);                                           // [CH_SCALE_SLOTS][MR]
+    half* cache = reinterpret_cast<half*>(smem + cx.L.off_cache);
+
+    pdl_launch_dependents();
+    if (warp == 0)
+    {
+        for (int i = lane; i < CH_NUM_BARS; i += 32)
+        {
+            int cnt = 1;
+            if (i >= CH_MAX_STAGES && i < 2 * CH_MAX_STAGES) cnt = 5;                   // W_EMPTY: 4 quad warps + MMA completion
+            else if (i >= 3 * CH_MAX_STAGES && i < 3 * CH_MAX_STAGES + 12) cnt = 4;     // SLOT_FULL: the quad's 4 warps
+            else if (i >= 3 * CH_MAX_STAGES + 32) cnt = 4;                              // D_EMPTY: the 4 epilogue warps
+            mbar_init(cx.bar0 + 8u * i, cnt);
+        }
+        fence_barrier_init();
+        tmem_alloc<512>(smem_u32(tmem_slot));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cx.tmem_base = *tmem_slot;
+
+    const int cta = blockIdx.x, G = gridDim.x;
+
+    if (warp == 0)
+    {
+        // =========================== TMA producer: never waits for an activation ===========================
+        Cursor c; c.init(ops, stages, p.n_stages, cta, G);
+        const uint64_t pol_w = policy_evict_first();
+        const uint32_t w_smem0 = smem_u32(smem);
+        int s = 0, ph = 0, cur_op = -1, K = 0;
+        const void* tm = nullptr;
+        while (c.valid)
+        {
+            if (c.op != cur_op)
+            {
+                cur_op = c.op; K = ops[cur_op].K;
+                tm = tmaps + cur_op;
+                if (elect_one()) prefetch_tmap(tm);
+            }
+            mbar_wait<64>(cx.W_EMPTY(s), ph ^ 1);
+            if (elect_one())
+            {
+                mbar_arrive_expect_tx(cx.W_FULL(s), (uint32_t) (2048 * K));
+                tma_load_2d(w_smem0 + s * p.w_bytes, tm, c.strip * (32 * K), c.kb * 8, cx.W_FULL(s), pol_w);
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+            c.next();
+        }
+        __syncwarp();
+    }
+    else if (warp < CH_DEC_WARP0)
+    {
+        // =========================== activation warps: scale pass per op, digits per unit ===========================
+        const int xw = warp - CH_XF_WARP0;
+        auto xf_bar = [] { asm volatile("bar.sync 2, 96;" ::: "memory"); };
+        pdl_wait();                                                   // external inputs come from the previous kernel
+        Cursor c; c.init(ops, stages, p.n_stages, cta, G);
+        int s = 0, ph = 0, cur_op = -1, waited = 0, turn = 0;
+        float inv_scale[CH_MR];
+        #pragma unroll
+        for (int r = 0; r < CH_MR; ++r) inv_scale[r] = 0.f;
+        while (c.valid)
+        {
+            const ChainOp& o = ops[c.op];
+            if (c.op != cur_op)
+            {
+                cur_op = c.op;
+                // ---- stage dependency: every output segment of the previous stage has been written ----
+                if (o.stage > waited)
+                {
+                    if (lane == 0)
+                    {
+                        const unsigned int want = (unsigned int) stages[o.stage - 1].strips_total;
+                        uint32_t polls = 0; unsigned long long t0 = 0;
+                        while (ld_acquire_gpu_u32(p.ctr + (o.stage - 1)) < want) { __nanosleep(64); ch_watchdog(polls, t0, "stage wait", o.stage, 0); }
+                    }
+                    __syncwarp();
+                    waited = o.stage;
+                }
+                xf_bar();                                             // previous op's cache no longer needed by any digit warp
+                if (warp == CH_XF_WARP0 && lane < CH_MR) s_norm2[lane] = 0u;
+                xf_bar();
+                // ---- scale pass: a = input row (silu * mul for the gated input), t = a * suh (fp16, as the reference's
+                //      A_had input), cache t, bound = max over 128-blocks of || t ||_2 ----
+                const int KB = o.KB;
+                for (int r = 0; r < o.m; ++r)
+                {
+                    float nmax = 0.f;
+                    for (int kb = xw; kb < KB; kb += CH_XF_WARPS)
+                    {
+                        const size_t e = (size_t) r * o.k + kb * 128 + lane * 4;
+                        half2 a, b;
+                        if (o.in_mode == 0)
+                        {
+                            const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
+                            a = *reinterpret_cast<const half2*>(&raw.x); b = *reinterpret_cast<const half2*>(&raw.y);
+                        }
+                        else if (o.in_mode == 1)
+                        {
+                            const float4 g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A) + e));
+                            const float4 u = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A2) + e));
+                            a = __floats2half2_rn(silu_f32(g.x) * u.x, silu_f32(g.y) * u.y);
+                            b = __floats2half2_rn(silu_f32(g.z) * u.z, silu_f32(g.w) * u.w);
+                        }
+                        else
+                        {
+                            const uint2 gr = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
+                            const uint2 ur = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A2) + e));
+                            const float2 g0 = __half22float2(*reinterpret_cast<const half2*>(&gr.x)), g1 = __half22float2(*reinterpret_cast<const half2*>(&gr.y));
+                            const float2 u0 = __half22float2(*reinterpret_cast<const half2*>(&ur.x)), u1 = __half22float2(*reinterpret_cast<const half2*>(&ur.y));
+                            a = __floats2half2_rn(silu_f32(g0.x) * u0.x, silu_f32(g0.y) * u0.y);
+                            b = __floats2half2_rn(silu_f32(g1.x) * u1.x, silu_f32(g1.y) * u1.y);
+                        }
+                        if (o.suh)
+                        {
+                            const uint2 scb = *reinterpret_cast<const uint2*>(o.suh + kb * 128 + lane * 4);
+                            a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
+                            b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
+                        }
+                        if (o.cached)
+                        {
+                            uint2 st; st.x = *reinterpret_cast<const uint32_t*>(&a); st.y = *reinterpret_cast<const uint32_t*>(&b);
+                            *reinterpret_cast<uint2*>(cache + (size_t) r * o.k + kb * 128 + lane * 4) = st;
+                        }
+                        const float2 fa = __half22float2(a), fb = __half22float2(b);
+                        float ss = fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+                        #pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+                        nmax = fmaxf(nmax, ss);
+                    }
+                    if (lane == 0) atomicMax(&s_norm2[r], __float_as_uint(nmax));
+                }
+                xf_bar();
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r)
+                {
+                    // bound on |xh|: block 2-norm, + margin for the fp32 reduction and the fp16 rounding of xh
+                    const float bnd = sqrtf(__uint_as_float(s_norm2[r])) * 1.002f;
+                    inv_scale[r] = bnd > 0.f ? (float) I8_QMAX / bnd : 0.f;
+                    // every digit warp stores the (identical) value before its own first X_FULL arrive of this op: whichever
+                    // arrive the MMA side observes, the scale the epilogue reads later is ordered before it
+                    if (lane == r) s_scale[(cur_op % CH_SCALE_SLOTS) * CH_MR + r] = bnd / (float) I8_QMAX;
+                }
+            }
+            if (turn == xw)
+            {
+                // ---- digits of this unit: 128-point Hadamard of the cached block, quantise, two int8 digits x 4 bytes ----
+                mbar_wait<64>(cx.W_EMPTY(s), ph ^ 1);
+                uint8_t* dst = smem + cx.L.off_b + s * CH_B_STAGE;
+                int qsum[CH_MR];
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r)
+                {
+                    qsum[r] = 0;
+                    if (r < o.m)
+                    {
+                        half2 a, b;
+                        if (o.cached)
+                        {
+                            const uint2 raw = *reinterpret_cast<const uint2*>(cache + (size_t) r * o.k + c.kb * 128 + lane * 4);
+                            a = *reinterpret_cast<const half2*>(&raw.x); b = *reinterpret_cast<const half2*>(&raw.y);
+                        }
+                        else
+                        {
+                            // rows too long for the cache: recompute the block (plain fp16 input only, checked on the host)
+                            const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + (size_t) r * o.k + c.kb * 128 + lane * 4));
+                            a = *reinterpret_cast<const half2*>(&raw.x); b = *reinterpret_cast<const half2*>(&raw.y);
+                            if (o.suh)
+                            {
+                                const uint2 scb = *reinterpret_cast<const uint2*>(o.suh + c.kb * 128 + lane * 4);
+                                a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
+                                b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
+                            }
+                        }
+                        float v0 = __low2float(a), v1 = __high2float(a), v2 = __low2float(b), v3 = __high2float(b);
+                        if (o.suh)
+                        {
+                            had128_warp(v0, v1, v2, v3, lane);
+                            a = __floats2half2_rn(v0 * R_SCALE, v1 * R_SCALE);
+                            b = __floats2half2_rn(v2 * R_SCALE, v3 * R_SCALE);
+                            v0 = __low2float(a); v1 = __high2float(a); v2 = __low2float(b); v3 = __high2float(b);
+                        }
+                        uint32_t hi_w[4], lo_w[4];
+                        int qs = 0;
+                        i8_digits(v0, inv_scale[r], qs, hi_w[0], lo_w[0]);
+                        i8_digits(v1, inv_scale[r], qs, hi_w[1], lo_w[1]);
+                        i8_digits(v2, inv_scale[r], qs, hi_w[2], lo_w[2]);
+                        i8_digits(v3, inv_scale[r], qs, hi_w[3], lo_w[3]);
+                        uint8_t* drow = dst + (lane * 8 + 2 * r) * 16;
+                        *reinterpret_cast<uint4*>(drow) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+                        *reinterpret_cast<uint4*>(drow + 16) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+                        qsum[r] = qs;
+                    }
+                }
+                #pragma unroll
+                for (int d = 16; d > 0; d >>= 1)
+                {
+                    #pragma unroll
+                    for (int r = 0; r < CH_MR; ++r) qsum[r] += __shfl_xor_sync(0xffffffffu, qsum[r], d);
+                }
+                if (lane < o.m)
+                {
+                    int mine = 0;
+                    #pragma unroll
+                    for (int r = 0; r < CH_MR; ++r) if (lane == r) mine = qsum[r];
+                    *reinterpret_cast<int*>(dst + CH_B_BYTES + 4 * lane) = mine;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(cx.X_FULL(s));
+            }
+            if (++turn == CH_XF_WARPS) turn = 0;
+            if (++s == S) { s = 0; ph ^= 1; }
+            c.next();
+        }
+    }
+    else if (warp < CH_EPI_WARP0)
+    {
+        // =========================== decode quads ===========================
+        const int q = warp & 3, Q = (warp - CH_DEC_WARP0) >> 2;
+        Cursor c; c.init(ops, stages, p.n_stages, cta, G);
+        QuadState qs; qs.slot = 0; qs.slph = 0; qs.dbuf = 0; qs.dph = 0; qs.acc = 0; qs.tsum = 0;
+        int s = 0, ph = 0;
+        while (c.valid)
+        {
+            if ((c.seq & 3) == Q)
+            {
+                int sb, se; c.sub_bounds(sb, se);
+                const bool first = c.seq - 4 < sb, last = c.seq + 4 >= se;
+                const int m = ops[c.op].m;
+                switch (ops[c.op].K)
+                {
+                    case 1: quad_unit<1>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 2: quad_unit<2>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 3: quad_unit<3>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 4: quad_unit<4>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 5: quad_unit<5>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 6: quad_unit<6>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 7: quad_unit<7>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    default: quad_unit<8>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                }
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+            c.next();
+        }
+    }
+    else
+    {
+        // =========================== epilogue ===========================
+        pdl_wait();
+        const int q = warp & 3;
+        const int et = threadIdx.x - CH_EPI_WARP0 * 32;
+        const int col = strip_col(q, lane);
+        const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+        float* tile = reinterpret_cast<float*>(smem + cx.L.off_tile);
+        auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+        const int part_stride = CH_MR * 128;
+        const float k_inv = __half2float(__ushort_as_half((unsigned short) 0x1eee));
+        const float k_bias = __half2float(__ushort_as_half((unsigned short) 0xc931));
+        const float c1 = 1534.0f * k_inv + k_bias;
+        int dbuf_bits = 0, dph_bits = 0;                                // per quad: bit Q
+        Cursor c; c.init(ops, stages, p.n_stages, cta, G);
+        while (c.valid)
+        {
+            const int op = c.op, strip = c.strip, stage = c.stage;
+            const ChainOp& o = ops[op];
+            const int run_begin = c.run_begin, run_end = c.run_end;
+            const long long U = stages[stage].U;
+            float* const parts = p.parts + (size_t) (stage & 1) * G * part_stride;
+            float facc[CH_MR];
+            #pragma unroll
+            for (int r = 0; r < CH_MR; ++r) facc[r] = 0.f;
+            for (int sb = run_begin; sb < run_end; sb += CH_SUB_UNITS)
+            {
+                const int se = sb + CH_SUB_UNITS < run_end ? sb + CH_SUB_UNITS : run_end;
+                long long dh[CH_MR], dl[CH_MR];
+                int T[CH_MR];
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r) { dh[r] = 0; dl[r] = 0; T[r] = 0; }
+                #pragma unroll
+                for (int Q = 0; Q < CH_QUADS; ++Q)
+                {
+                    // does quad Q own a unit of [sb, se)?  first such unit: sb + ((Q - sb) & 3)
+                    if (sb + ((Q - sb) & 3) < se)
+                    {
+                        const int b = (dbuf_bits >> Q) & 1, ph = (dph_bits >> Q) & 1;
+                        mbar_wait<32>(cx.D_FULL(Q, b), ph);
+                        tc_fence_after();
+                        uint32_t rr[16];
+                        tmem_ld_32x32b_x16(cx.tmem_base + lane_base + CH_D_COL0 + (Q * 2 + b) * CH_NT, rr);
+                        tc_wait_ld();
+                        #pragma unroll
+                        for (int r = 0; r < CH_MR; ++r)
+                        {
+                            dh[r] += (int) rr[2 * r]; dl[r] += (int) rr[2 * r + 1];
+                            T[r] += s_tout[(Q * 2 + b) * CH_MR + r];
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(cx.D_EMPTY(Q, b));
+                        dbuf_bits ^= 1 << Q;
+                        if (b == 1) dph_bits ^= 1 << Q;
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r)
+                {
+                    if (r < o.m)
+                    {
+                        const long long sp = 256ll * dh[r] + dl[r] - 510ll * T[r];
+                        facc[r] += i8_assemble(sp, T[r], s_scale[(op % CH_SCALE_SLOTS) * CH_MR + r], k_inv, c1);
+                    }
+                }
+            }
+
+            // who else holds k-segments of this strip?
+            const long long gs = o.unit_off + (long long) strip * o.KB;
+            const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + o.KB - 1);
+            const bool full = c_a == c_b;
+            bool emit = full;
+            if (full)
+            {
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r) if (r < o.m) tile[r * 128 + col] = facc[r];
+            }
+            else if (cta != c_a)
+            {
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r)
+                    if (r < o.m)
+                    {
+                        uint32_t bits = __float_as_uint(facc[r]);
+                        if (bits == CH_SENTINEL) bits = 0x7fc00000u;
+                        st_relaxed_gpu_u32(reinterpret_cast<uint32_t*>(parts + (size_t) cta * part_stride + r * 128 + col), bits);
+                    }
+            }
+            else
+            {
+                #pragma unroll
+                for (int r = 0; r < CH_MR; ++r)
+                {
+                    if (r < o.m)
+                    {
+                        float a = facc[r];
+                        int cc0 = c_a + 1;
+                        while (cc0 <= c_b)
+                        {
+                            uint32_t v[8];
+                            bool ok;
+                            uint32_t polls = 0; unsigned long long t0 = 0;
+                            do
+                            {
+                                ok = true;
+                                #pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                {
+                                    const int cc = cc0 + j;
+                                    v[j] = 0u;
+                                    if (cc <= c_b)
+                                    {
+                                        v[j] = ld_relaxed_gpu_u32(reinterpret_cast<const uint32_t*>(parts + (size_t) cc * part_stride + r * 128 + col));
+                                        ok = ok && v[j] != CH_SENTINEL;
+                                    }
+                                }
+                                if (!ok) ch_watchdog(polls, t0, "split-K exchange", stage, strip);
+                            } while (!ok);
+                            #pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                            {
+                                const int cc = cc0 + j;
+                                if (cc <= c_b)
+                                {
+                                    a += __uint_as_float(v[j]);
+                                    st_relaxed_gpu_u32(reinterpret_cast<uint32_t*>(parts + (size_t) cc * part_stride + r * 128 + col), CH_SENTINEL);
+                                }
+                            }
+                            cc0 += 8;
+                        }
+                        tile[r * 128 + col] = a;
+                    }
+                }
+                emit = true;
+            }
+            if (emit)
+            {
+                epi_bar();
+                for (int r = q; r < o.m; r += 4)
+                    output_row_128(tile + r * 128, (char*) o.C, (size_t) r * o.n + strip * 128,
+                                   o.svh ? o.svh + strip * 128 : nullptr, o.out_scale, o.c_fp32 != 0, lane);
+                epi_bar();
+                if (et == 0)
+                {
+                    __threadfence();
+                    atomicAdd(p.ctr + stage, 1u);
+                }
+            }
+            // skip to the first unit after this run
+            const int run_len = run_end - run_begin;
+            for (int i = 0; i < run_len; ++i) c.next();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+    {
+        tc_fence_after();
+        tmem_dealloc<512>(cx.tmem_base);
+    }
+    if (threadIdx.x == 0)
+    {
+        // last CTA out re-zeroes the counters for the next launch (which reads them only after griddepcontrol.wait)
+        __threadfence();
+        const unsigned int t = atomicAdd(p.ctr + p.n_stages, 1u);
+        if (t == gridDim.x - 1)
+        {
+            for (int i = 0; i <= p.n_stages; ++i) p.ctr[i] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+
+struct Chain
+{
+    int device = -1;
+    std::vector<ChainOp> ops;
+    std::vector<ChainStage> stages;
+    std::vector<CUtensorMap> tmaps;
+    void* d_blob = nullptr;             // device copy: tmaps | ops | stages
+    ChainParams p{};
+    int smem_total = 0, grid = 0;
+};
+
+const char* chain_op_unsupported(int m, int k, int n, int K, int cb, int in_mode)
+{
+    if (cb != 2) return "needs the mul1 codebook";
+    if (m < 1 || m > CH_MR) return "needs 1 <= m <= 4";
+    if (K < 1 || K > 8) return "K out of range";
+    if (k < 128 || n < 128 || k % 128 || n % 128) return "k and n must be multiples of 128";
+    if (in_mode < 0 || in_mode > 2) return "in_mode must be 0 (fp16 rows), 1 (silu(gate) * up, fp32) or 2 (same, fp16)";
+    if (in_mode != 0 && (size_t) m * k * 2 > CH_CACHE_MAX) return "gated input needs m * k <= 32768";
+    return nullptr;
+}
+
+// Fill ops / stages / launch geometry from the caller's list.  Pure host arithmetic (also behind exl3b_chain_plan).
+static int chain_build(const exl3b_chain_op* in, int n_ops, int num_sms, Chain& ch)
+{
+    EXL3B_CHECK(in && n_ops >= 1, EXL3B_ERR_ARG, "exl3_chain: empty op list");
+    EXL3B_CHECK(n_ops <= 4096, EXL3B_ERR_ARG, "exl3_chain: too many ops");
+    ch.ops.resize(n_ops);
+    ch.stages.clear();
+    int Kmax = 1;
+    size_t cache = 0;
+    long long Umax = 0;
+    for (int i = 0; i < n_ops; ++i)
+    {
+        const exl3b_chain_op& a = in[i];
+        const char* why = chain_op_unsupported(a.m, a.k, a.n, a.K, a.cb, a.in_mode);
+        EXL3B_CHECK(!why, EXL3B_ERR_UNSUPPORTED, "exl3_chain: op %d: %s", i, why ? why : "");
+        EXL3B_CHECK(a.A && a.B && a.C && (a.in_mode == 0 || a.A2), EXL3B_ERR_ARG, "exl3_chain: op %d: null tensor", i);
+        if (i == 0 || a.new_stage)
+        {
+            ChainStage st{};
+            st.op_begin = i; st.op_end = i; st.U = 0; st.strips_total = 0;
+            ch.stages.push_back(st);
+        }
+        ChainStage& st = ch.stages.back();
+        ChainOp& o = ch.ops[i];
+        o = ChainOp{};
+        o.A = a.A; o.A2 = a.A2; o.suh = (const half*) a.suh; o.svh = (const half*) a.svh; o.C = a.C;
+        o.m = a.m; o.k = a.k; o.n = a.n; o.K = a.K; o.c_fp32 = a.c_fp32 != 0; o.in_mode = a.in_mode;
+        o.KB = a.k / 128; o.strips = a.n / 128; o.stage = (int) ch.stages.size() - 1;
+        o.unit_off = st.U; o.out_scale = 1.0f;
+        const size_t cb_ = ((size_t) a.m * a.k * 2 + 127) / 128 * 128;
+        o.cached = cb_ <= (size_t) CH_CACHE_MAX;
+        if (o.cached && cb_ > cache) cache = cb_;
+        st.U += (long long) o.KB * o.strips; st.strips_total += o.strips; st.op_end = i + 1;
+        if (a.K > Kmax) Kmax = a.K;
+    }
+    EXL3B_CHECK(ch.stages.size() <= 255, EXL3B_ERR_UNSUPPORTED, "exl3_chain: more than 255 stages");
+    for (const ChainStage& st : ch.stages) if (st.U > Umax) Umax = st.U;
+    const int w_bytes = 2048 * Kmax;
+    int S = (220 * 1024 - 128 - CH_MR * 128 * 4 - 2048 - (int) cache) / (w_bytes + CH_B_STAGE);
+    if (S > CH_MAX_STAGES) S = CH_MAX_STAGES;
+    EXL3B_CHECK(S >= 2, EXL3B_ERR_UNSUPPORTED, "exl3_chain: shared-memory budget exceeded");
+    const ChainSmem L = chain_smem(S, w_bytes, (int) cache);
+    EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_chain: shared-memory budget exceeded");
+    int grid = num_sms;
+    if (Umax < grid) grid = (int) Umax;
+    EXL3B_CHECK(grid <= DevCtx::I8_PART_CTAS, EXL3B_ERR_UNSUPPORTED, "exl3_chain: grid exceeds the split-K exchange buffer");
+    ch.p = ChainParams{};
+    ch.p.n_ops = n_ops; ch.p.n_stages = (int) ch.stages.size();
+    ch.p.S = S; ch.p.w_bytes = w_bytes; ch.p.cache_bytes = (int) cache;
+    ch.smem_total = L.total; ch.grid = grid;
+    return 0;
+}
+
+static cudaError_t chain_launch(cudaStream_t stream, int grid, int smem_bytes, const ChainParams& p)
+{
+    static bool attr_set[32] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_set[dev & 31])
+    {
+        cudaError_t e = cudaFuncSetAttribute(chain_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 31] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, chain_i8_kernel, p);
+}
+
+int chain_plan(const exl3b_chain_op* in, int n_ops, int num_sms, struct exl3b_chain_plan* out)
+{
+    Chain ch;
+    int r = chain_build(in, n_ops, num_sms, ch); if (r) return r;
+    out->stages = ch.p.n_stages; out->grid = ch.grid; out->ring_stages = ch.p.S; out->smem_bytes = ch.smem_total;
+    out->cache_bytes = ch.p.cache_bytes; out->units = 0;
+    for (const ChainStage& st : ch.stages) out->units += st.U;
+    return 0;
+}
+
+// host-side replay of one CTA's walk with the kernel's own Cursor (tests: every unit visited exactly once, run bounds)
+int chain_walk(const exl3b_chain_op* in, int n_ops, int num_sms, int cta, int32_t* out, int max_units)
+{
+    Chain ch;
+    int r = chain_build(in, n_ops, num_sms, ch); if (r) return r;
+    EXL3B_CHECK(cta >= 0 && cta < ch.grid && out && max_units >= 0, EXL3B_ERR_ARG, "exl3_chain_walk: bad argument");
+    Cursor c; c.init(ch.ops.data(), ch.stages.data(), ch.p.n_stages, cta, ch.grid);
+    int n = 0;
+    while (c.valid)
+    {
+        if (n < max_units)
+        {
+            int sb, se; c.sub_bounds(sb, se);
+            int32_t* o = out + (size_t) n * 8;
+            o[0] = c.stage; o[1] = c.op; o[2] = c.strip; o[3] = c.kb; o[4] = c.seq; o[5] = c.run_begin; o[6] = c.run_end; o[7] = sb * 65536 + (se - sb);
+        }
+        ++n;
+        c.next();
+    }
+    return n;
+}
+
+int chain_create(DevCtx* ctx, const exl3b_chain_op* in, int n_ops, void** out)
+{
+    EXL3B_CHECK(out, EXL3B_ERR_ARG, "exl3_chain_create: null output");
+    Chain* ch = new Chain();
+    int r = chain_build(in, n_ops, ctx->num_sms, *ch);
+    if (r) { delete ch; return r; }
+    ch->device = ctx->device;
+    ch->tmaps.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i)
+    {
+        r = get_weight_tmap(in[i].B, in[i].k, in[i].n, in[i].K, &ch->tmaps[i]);
+        if (r) { delete ch; return r; }
+    }
+    const size_t b_tm = sizeof(CUtensorMap) * n_ops, b_ops = sizeof(ChainOp) * n_ops, b_st = sizeof(ChainStage) * ch->stages.size();
+    if (cudaMalloc(&ch->d_blob, b_tm + b_ops + b_st) != cudaSuccess) { delete ch; return fail(EXL3B_ERR_CUDA, "exl3_chain_create: cudaMalloc failed"); }
+    uint8_t* d = (uint8_t*) ch->d_blob;
+    cudaError_t e = cudaMemcpy(d, ch->tmaps.data(), b_tm, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + b_tm, ch->ops.data(), b_ops, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + b_tm + b_ops, ch->stages.data(), b_st, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(ch->d_blob); delete ch; return fail(EXL3B_ERR_CUDA, "exl3_chain_create: %s", cudaGetErrorString(e)); }
+    ch->p.tmaps = (const CUtensorMap*) d; ch->p.ops = (const ChainOp*) (d + b_tm); ch->p.stages = (const ChainStage*) (d + b_tm + b_ops);
+    ch->p.n_inline = 0;
+    ch->p.ctr = ctx->chain_ctr; ch->p.parts = ctx->chain_parts;
+    *out = ch;
+    return 0;
+}
+
+int chain_run(cudaStream_t stream, void* chain)
+{
+    Chain* ch = (Chain*) chain;
+    EXL3B_CHECK(ch, EXL3B_ERR_ARG, "exl3_chain_run: null chain");
+    int dev = -1; EXL3B_CUDA(cudaGetDevice(&dev));
+    EXL3B_CHECK(dev == ch->device, EXL3B_ERR_ARG, "exl3_chain_run: chain was created on device %d, current device is %d", ch->device, dev);
+    ch->p.dbg = g_tc_dbg;
+    cudaError_t err = chain_launch(stream, ch->grid, ch->smem_total, ch->p);
+    count_launch();
+    EXL3B_CUDA(err);
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return EXL3B_TAG_TC_I8_CHAIN;
+}
+
+int chain_destroy(void* chain)
+{
+    Chain* ch = (Chain*) chain;
+    if (!ch) return 0;
+    if (ch->d_blob) cudaFree(ch->d_blob);
+    delete ch;
+    return 0;
+}
+
+bool gemm_chain_supported(const GemmArgs& a)
+{
+    return chain_op_unsupported(a.m, a.k, a.n, a.K, a.cb, 0) == nullptr;
+}
+
+// a single exl3_gemm on the chain kernel: the op travels in the kernel parameters, nothing is allocated or copied
+int launch_gemm_chain(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
+{
+    exl3b_chain_op in{};
+    in.A = a.A; in.B = a.B; in.suh = a.suh; in.svh = a.svh; in.C = a.C;
+    in.m = a.m; in.k = a.k; in.n = a.n; in.K = a.K; in.cb = a.cb; in.c_fp32 = a.c_fp32; in.in_mode = 0; in.new_stage = 0;
+    Chain ch;
+    { int r = chain_build(&in, 1, a.max_ctas > 0 && a.max_ctas < ctx->num_sms ? a.max_ctas : ctx->num_sms, ch); if (r) return r; }
+    ch.ops[0].out_scale = a.out_scale;
+    ChainParams& p = ch.p;
+    { int r = get_weight_tmap(a.B, a.k, a.n, a.K, &p.tmaps_inline[0]); if (r) return r; }
+    p.ops_inline[0] = ch.ops[0]; p.stages_inline[0] = ch.stages[0];
+    p.n_inline = 1; p.ctr = ctx->chain_ctr; p.parts = ctx->chain_parts; p.dbg = g_tc_dbg;
+    cudaError_t err = chain_launch(stream, ch.grid, ch.smem_total, p);
+    count_launch();
+    EXL3B_CUDA(err);
+    EXL3B_CUDA(cudaPeekAtLastError());
+    return EXL3B_TAG_TC_I8_CHAIN;
+}
+
+}  // namespace exl3b

@@ -58,6 +58,10 @@ struct DevCtx
     float* i8_parts = nullptr;
     static constexpr int I8_PART_CTAS = 256;
     float* i8_parts_slot(int s) { return i8_parts + (size_t) s * I8_PART_CTAS * 1024; }
+    // chain kernel (chain_i8.cu): stage counters + exit ticket (zero between launches) and its split-K exchange
+    // [2][I8_PART_CTAS][4 x 128] (sentinel between launches); shared by all chains of the device (one in-order stream)
+    unsigned int* chain_ctr = nullptr;
+    float* chain_parts = nullptr;
     // Launch slots rotate per device, not per stream: launches issued concurrently on two streams of one device (or from two
     // host threads: ctypes releases the GIL) get distinct slots from this atomic counter, but more than NUM_SLOTS launches in
     // flight on one device would share split-K scratch -- the library supports ONE in-order stream of qgemm launches per
@@ -140,6 +144,15 @@ struct MGemmArgs
     const int32_t* size_n_list; const uint64_t* c_ptrs; int num_c_ptrs;
 };
 int launch_mgemm(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
+
+// persistent multi-GEMM kernel (chain_i8.cu)
+bool gemm_chain_supported(const GemmArgs& a);
+int launch_gemm_chain(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a);
+int chain_plan(const exl3b_chain_op* in, int n_ops, int num_sms, struct exl3b_chain_plan* out);
+int chain_walk(const exl3b_chain_op* in, int n_ops, int num_sms, int cta, int32_t* out, int max_units);
+int chain_create(DevCtx* ctx, const exl3b_chain_op* in, int n_ops, void** out);
+int chain_run(cudaStream_t stream, void* chain);
+int chain_destroy(void* chain);
 int launch_mgemm_resolve(cudaStream_t stream, MSlotTable* tab, const MGemmArgs& a, int bszm);
 int launch_mgemm_reduce(cudaStream_t stream, DevCtx* ctx, const MSlotTable* tab, const MGemmArgs& a);
 // routed / weighted exl3_mgemm (MoE decode) on the tcgen05 int8 path (gemm_tc_i8_routed.cu): opt-in, tag EXL3B_TAG_TC_I8_ROUTED

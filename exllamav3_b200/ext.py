@@ -65,11 +65,29 @@ _lib.exl3b_tp_debug_inject.argtypes = [_vp, _i, _vp, _i64]; _lib.exl3b_tp_debug_
 _lib.exl3b_tp_debug_peek.argtypes = [_i, _i, _i, _vp, _i64]; _lib.exl3b_tp_debug_peek.restype = _i
 _lib.exl3b_tp_debug_epoch.restype = _i64
 
+
+
+class _ChainOp(ctypes.Structure):
+    _fields_ = [("A", _vp), ("A2", _vp), ("B", _vp), ("suh", _vp), ("svh", _vp), ("C", _vp),
+                ("m", _i), ("k", _i), ("n", _i), ("K", _i), ("cb", _i), ("c_fp32", _i), ("in_mode", _i), ("new_stage", _i)]
+
+
+class _ChainPlan(ctypes.Structure):
+    _fields_ = [("stages", _i), ("grid", _i), ("ring_stages", _i), ("smem_bytes", _i), ("cache_bytes", _i), ("units", _i64)]
+
+
+_lib.exl3b_chain_plan.argtypes = [ctypes.POINTER(_ChainOp), _i, _i, ctypes.POINTER(_ChainPlan)]; _lib.exl3b_chain_plan.restype = _i
+_lib.exl3b_chain_walk.argtypes = [ctypes.POINTER(_ChainOp), _i, _i, _i, _vp, _i]; _lib.exl3b_chain_walk.restype = _i
+_lib.exl3b_chain_create.argtypes = [ctypes.POINTER(_ChainOp), _i, ctypes.POINTER(_vp)]; _lib.exl3b_chain_create.restype = _i
+_lib.exl3b_chain_run.argtypes = [_vp, _vp]; _lib.exl3b_chain_run.restype = _i
+_lib.exl3b_chain_destroy.argtypes = [_vp]; _lib.exl3b_chain_destroy.restype = _i
+
 assert _lib.exl3b_abi_version() == 1
 
 EXL3B_TAG_SIMT = 100
 EXL3B_TAG_TC = 200
 EXL3B_TAG_TC_I8 = 210
+EXL3B_TAG_TC_I8_CHAIN = 220
 EXL3B_TAG_TC_I8_AR = 211
 EXL3B_TAG_TC_I8_ROUTED = 212
 TP_HANDLE_BYTES = 64
@@ -115,7 +133,7 @@ def launch_count() -> int:
 
 
 def set_gemm_path(tag: int) -> int:
-    """0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC.  Returns the previous setting."""
+    """0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC, EXL3B_TAG_TC_I8, EXL3B_TAG_TC_I8_CHAIN.  Returns the previous setting."""
     return int(_lib.exl3b_set_gemm_path(int(tag)))
 
 
@@ -146,6 +164,84 @@ def exl3_gemm(A, B, C, suh, A_had, svh, force_shape_idx: int, mcg, mul1, force_n
         return _check(_lib.exl3b_gemm(
             _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had) if suh is not None else None, _ptr(svh),
             size_m, size_k, size_n, K, _cb(mcg, mul1), int(c_fp32), int(force_shape_idx), int(force_num_sms)))
+
+
+# ---- GEMM chains: the quantized linears of a decode block as ONE persistent launch (include/exl3b200.h) --------------------
+
+class GemmChain:
+    """
+    The launch sequences of the reference's C++ block modules as one kernel: BC_GatedMLP's exl3_mgemm(gate, up) -> silu_mul ->
+    exl3_gemm(down) (exllamav3_ext/libtorch/mlp.cpp:14-91) and BC_Attention's q / k / v projections
+    (libtorch/attention.cpp:286-365).  `ops` is a list of dicts, executed in order:
+        x        (m, k) fp16 input rows,          or   gate=, up=   (m, k) fp32|fp16 outputs of earlier ops: input = silu(gate) * up
+        trellis, suh, svh, y                       as exl3_gemm's B, suh, svh, C (y fp16 or fp32, (m, n))
+        mcg / mul1                                 codebook flags (only mul1 is eligible)
+        new_stage                                  True: this op (and the following ones) may read outputs of earlier ops
+    Construction validates like exl3_gemm and copies the table to the device (do it once, outside graph capture); run() is one
+    asynchronous launch on the current stream.  Holds references to every tensor.
+    """
+
+    def __init__(self, ops: list):
+        if not ops:
+            raise RuntimeError("GemmChain: empty op list")
+        arr = (_ChainOp * len(ops))()
+        self._keep = []
+        dev = None
+        for i, o in enumerate(ops):
+            tr, y = o["trellis"], o["y"]
+            gated = "gate" in o
+            x = o["gate"] if gated else o["x"]
+            x2 = o["up"] if gated else None
+            _need_cuda(x, x2, tr, y, o.get("suh"), o.get("svh"))
+            if tr.dim() != 3:
+                raise RuntimeError("B: incorrect number of dimensions, must be 3")
+            _dtype(tr, torch.int16, "B")
+            if gated:
+                if x.dtype not in (torch.float, torch.half) or x2.dtype != x.dtype or x2.shape != x.shape:
+                    raise RuntimeError("gate / up must be fp32 or fp16 tensors of one shape")
+                in_mode = 1 if x.dtype == torch.float else 2
+            else:
+                _dtype(x, torch.half, "A")
+                in_mode = 0
+            c_fp32 = y.dtype == torch.float
+            if not c_fp32:
+                _dtype(y, torch.half, "C")
+            k = x.shape[-1]
+            m = x.numel() // k if k else 0
+            n, K = tr.shape[1] * 16, tr.shape[2] // 16
+            if k != tr.shape[0] * 16:
+                raise RuntimeError("A and B incompatible shapes")
+            if y.shape[-1] != n or y.numel() != m * n:
+                raise RuntimeError("C and B incompatible shapes")
+            assert x.is_contiguous() and tr.is_contiguous() and y.is_contiguous() and (x2 is None or x2.is_contiguous())
+            if dev is None:
+                dev = tr.device
+            elif tr.device != dev:
+                raise RuntimeError("GemmChain: all tensors must live on one device")
+            a = arr[i]
+            a.A, a.A2, a.B, a.suh, a.svh, a.C = _ptr(x), _ptr(x2), _ptr(tr), _ptr(o.get("suh")), _ptr(o.get("svh")), _ptr(y)
+            a.m, a.k, a.n, a.K, a.cb, a.c_fp32 = m, k, n, K, _cb(o.get("mcg", False), o.get("mul1", False)), int(c_fp32)
+            a.in_mode, a.new_stage = in_mode, int(bool(o.get("new_stage", False)))
+            self._keep.append((x, x2, tr, o.get("suh"), o.get("svh"), y))
+        self.device, self.n_ops = dev, len(ops)
+        self._h = _vp()
+        with torch.cuda.device(dev):
+            _check(_lib.exl3b_chain_create(arr, len(ops), ctypes.byref(self._h)))
+
+    def run(self) -> int:
+        with torch.cuda.device(self.device):
+            return _check(_lib.exl3b_chain_run(torch.cuda.current_stream(self.device).cuda_stream, self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.exl3b_chain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- tensor-parallel row-parallel output: GEMM + sum over ranks in one kernel (include/exl3b200.h) --------------------

@@ -56,6 +56,7 @@ enum exl3b_status
 #define EXL3B_TAG_TC 200       /* tcgen05 / TMEM decode-GEMM, bit-exact fp16 weights       */
 #define EXL3B_TAG_TC_I8 210    /* tcgen05 kind::i8 codebook path: mul1, m <= 4 (auto); m <= 8 with m*k <= 32768 when forced */
 #define EXL3B_TAG_TC_I8_ROUTED 212 /* routed / weighted exl3b_mgemm (MoE decode) on the kind::i8 kernel: mul1, m <= 4 (auto) */
+#define EXL3B_TAG_TC_I8_CHAIN 220 /* persistent multi-GEMM kernel (exl3b_chain_*; exl3b_gemm when forced): mul1, m <= 4 */
 #define EXL3B_TAG_TC_I8_AR 211 /* the same kernel with the tensor-parallel sum fused into its epilogue (exl3b_gemm_allreduce) */
 
 int exl3b_abi_version(void);
@@ -143,6 +144,45 @@ int exl3b_mgemm(void* stream,
                 int min_index, int max_index, int num_tokens,
                 const int32_t* size_n_list, const uint64_t* c_ptrs, int num_c_ptrs,
                 int force_shape_idx, int force_num_sms);
+
+/*
+ * ---- GEMM chains: one persistent launch for the quantized linears of a decode block ------------------------------------
+ *
+ * The reference runs the linears of a block as separate graph nodes of its C++ block modules: BC_GatedMLP issues
+ * exl3_mgemm(gate, up) -> silu_mul -> exl3_gemm(down) (exllamav3_ext/libtorch/mlp.cpp:14-91), BC_Attention the q / k / v
+ * projections and, after attention, o (exllamav3_ext/libtorch/attention.cpp:286-365).  A chain is the drop-in for those
+ * launch sequences: a list of exl3_gemm-shaped ops executed by ONE persistent kernel whose weight stream does not stop at a
+ * GEMM boundary (chain_i8.cu).  Ops are grouped into stages: an op with new_stage != 0 starts a stage whose inputs may be
+ * outputs of earlier ops of the chain (a grid-wide dependency inside the kernel); ops of one stage are independent.
+ *   A / A2 / in_mode   0: A = (m, k) fp16 input rows;  1: input = silu(A) * A2 with A = gate, A2 = up outputs, fp32 (m, k);
+ *                      2: the same with fp16 gate / up  (the activation the reference applies between gate/up and down,
+ *                      activation_kernels.cuh:144-240, folded into down's input stage; result rounded to fp16 as there)
+ *   B, suh, svh, C, m, k, n, K, cb, c_fp32   as exl3b_gemm (no A_had: the transform runs inside the kernel)
+ * Eligibility per op: mul1 codebook, 1 <= m <= 4, k % 128 == n % 128 == 0; otherwise -EXL3B_ERR_UNSUPPORTED from create.
+ * exl3b_chain_create copies the op table to the device (synchronous: call it outside stream capture, once per block, like the
+ * reference constructs its BC_* modules once); exl3b_chain_run is one asynchronous launch, capturable in a CUDA graph;
+ * returns EXL3B_TAG_TC_I8_CHAIN.  One chain runs at a time per device (stream order).
+ * exl3b_chain_plan: host-only introspection (stages, persistent grid, ring depth, shared memory) for tests.
+ */
+struct exl3b_chain_op
+{
+    const void* A; const void* A2; const void* B; const void* suh; const void* svh; void* C;
+    int m, k, n, K, cb, c_fp32;
+    int in_mode;
+    int new_stage;
+};
+struct exl3b_chain_plan
+{
+    int stages, grid, ring_stages, smem_bytes, cache_bytes;
+    int64_t units;
+};
+int exl3b_chain_plan(const struct exl3b_chain_op* ops, int n_ops, int num_sms, struct exl3b_chain_plan* out);
+/* tests: replay CTA `cta`'s walk over its units with the kernel's own cursor; 8 int32 per unit: stage, op, strip, kb, seq,
+   run_begin, run_end, chunk_begin * 65536 + chunk_len.  Returns the number of units of that CTA (may exceed max_units). */
+int exl3b_chain_walk(const struct exl3b_chain_op* ops, int n_ops, int num_sms, int cta, int32_t* out, int max_units);
+int exl3b_chain_create(const struct exl3b_chain_op* ops, int n_ops, void** chain);
+int exl3b_chain_run(void* stream, void* chain);
+int exl3b_chain_destroy(void* chain);
 
 /*
  * exl3b_reconstruct -- replaces ext.reconstruct / ext.reconstruct_slice (exllamav3_ext/bindings.cpp:122-123,
