@@ -102,6 +102,7 @@ struct Cursor
 {
     const ChainOp* ops; const ChainStage* stages;
     int n_stages, cta, G;
+    int Gs;                   // CTAs that share the current stage: min(G, units of the stage), so that no CTA range is empty
     int stage, op, strip, kb, KB, strips;
     long long u, uend;
     int seq;                  // running index of the unit on this CTA over the whole chain: ring stage, quad, digit warp
@@ -121,8 +122,9 @@ struct Cursor
         while (++stage < n_stages)
         {
             const long long U = stages[stage].U;
-            const long long ub = unit_begin(U, G, cta), ue = unit_begin(U, G, cta + 1);
-            if (ue <= ub) continue;
+            Gs = U < G ? (int) U : G;
+            if (cta >= Gs) continue;
+            const long long ub = unit_begin(U, Gs, cta), ue = unit_begin(U, Gs, cta + 1);
             u = ub; uend = ue;
             op = stages[stage].op_begin;
             while (u >= ops[op].unit_off + (long long) ops[op].KB * ops[op].strips) ++op;
@@ -213,6 +215,8 @@ struct ChainCtx
     int S, w_bytes;
     ChainSmem L;
     uint32_t tmem_base;
+    unsigned long long* dbg;
+    int trace_seq;            // bring-up: the unit (CTA-local index) whose rounds are stamped
     __device__ __forceinline__ uint32_t W_FULL(int s) const { return bar0 + 8u * s; }
     __device__ __forceinline__ uint32_t W_EMPTY(int s) const { return bar0 + 8u * (CH_MAX_STAGES + s); }
     __device__ __forceinline__ uint32_t X_FULL(int s) const { return bar0 + 8u * (2 * CH_MAX_STAGES + s); }
@@ -223,11 +227,18 @@ struct ChainCtx
 };
 constexpr int CH_NUM_BARS = 3 * CH_MAX_STAGES + 40;                    // 88 barriers = 704 B
 
+#ifdef EXL3B_TC_DEBUG
+#define CH_STAMP(cond, slot) do { if ((cond) && cx.dbg) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__) :: "memory"); cx.dbg[blockIdx.x * 64 + (slot)] = t__; } } while (0)
+#else
+#define CH_STAMP(cond, slot) do { } while (0)
+#endif
+
 // One unit (128 k x 128 n weights) of a decode quad: four rounds of two k-tiles.
 template <int K>
 __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int Q, int q, int lane, int s, int wph,
-                                          bool first, bool last, int m, int* s_tout)
+                                          bool first, bool last, int m, int* s_tout, [[maybe_unused]] bool trace)
 {
+    [[maybe_unused]] const bool tr_l = trace && q == 0 && lane == 0, tr_n = trace && q == 1 && lane == 0;
     const int tl = strip_tile(q, lane), chunk = lane & 7;
     const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
     const uint32_t lane_base = (uint32_t) (q * 32) << 16;
@@ -244,9 +255,12 @@ __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int
     for (int tp = 0; tp < 4; ++tp)
     {
         uint32_t w[2][K + 1];
+        CH_STAMP(tr_l, tp * 8 + 0); CH_STAMP(tr_n, 32 + tp * 6 + 0);
         ch_load_tiles2<K>(wst, tl, chunk, prev_lane, 2 * tp, w);
+        CH_STAMP(tr_l, tp * 8 + 1); CH_STAMP(tr_n, 32 + tp * 6 + 1);
         mbar_wait(cx.SLOT_EMPTY(Q, qs.slot), qs.slph ^ 1);
         tc_fence_after();
+        CH_STAMP(tr_l, tp * 8 + 2); CH_STAMP(tr_n, 32 + tp * 6 + 2);
         const uint32_t a_col = (uint32_t) ((Q * CH_SLOTS + qs.slot) * CH_SLOT_COLS);
         #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -255,7 +269,9 @@ __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int
             if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
             tmem_st_32x32b_x16(cx.tmem_base + lane_base + a_col + 16 * j, o);
         }
+        CH_STAMP(tr_l, tp * 8 + 3); CH_STAMP(tr_n, 32 + tp * 6 + 3);
         tc_wait_st();
+        CH_STAMP(tr_l, tp * 8 + 4); CH_STAMP(tr_n, 32 + tp * 6 + 4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0)
@@ -263,6 +279,7 @@ __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int
             mbar_arrive(cx.SLOT_FULL(Q, qs.slot));
             if (tp == 3) mbar_arrive(cx.W_EMPTY(s));
         }
+        CH_STAMP(tr_l, tp * 8 + 5); CH_STAMP(tr_n, 32 + tp * 6 + 5);
         if (lead)
         {
             if (tp == 0)
@@ -278,6 +295,7 @@ __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int
             }
             mbar_wait(cx.SLOT_FULL(Q, qs.slot), qs.slph);
             tc_fence_after();
+            CH_STAMP(tr_l, tp * 8 + 6);
             const bool fin = tp == 3 && last;
             if (fin)
             {
@@ -302,6 +320,7 @@ __device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int
             }
             qs.acc = 1;
             __syncwarp();
+            CH_STAMP(tr_l, tp * 8 + 7);
             desc_lo += 64;
             if (fin) { qs.dbuf ^= 1; if (qs.dbuf == 0) qs.dph ^= 1; }
         }
@@ -331,6 +350,8 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
     const int S = p.S;
     ChainCtx cx;
     cx.smem = smem; cx.S = S; cx.w_bytes = p.w_bytes; cx.L = chain_smem(S, p.w_bytes, p.cache_bytes);
+    cx.dbg = p.dbg; cx.trace_seq = 8;
+    CH_STAMP(threadIdx.x == 0, 61);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cx.L.off_bars);
     cx.bar0 = smem_u32(bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cx.L.off_bars + 8 * CH_NUM_BARS);              // +704
@@ -416,6 +437,7 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                     __syncwarp();
                     waited = o.stage;
                 }
+                CH_STAMP(warp == CH_XF_WARP0 && lane == 0 && c.seq == 0, 59);
                 xf_bar();                                             // previous op's cache no longer needed by any digit warp
                 if (warp == CH_XF_WARP0 && lane < CH_MR) s_norm2[lane] = 0u;
                 xf_bar();
@@ -425,47 +447,68 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                 for (int r = 0; r < o.m; ++r)
                 {
                     float nmax = 0.f;
-                    for (int kb = xw; kb < KB; kb += CH_XF_WARPS)
+                    // four blocks per step, their loads in flight together (one L2 round trip per step, not per block)
+                    for (int kb0 = xw; kb0 < KB; kb0 += 4 * CH_XF_WARPS)
                     {
-                        const size_t e = (size_t) r * o.k + kb * 128 + lane * 4;
-                        half2 a, b;
-                        if (o.in_mode == 0)
-                        {
-                            const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
-                            a = *reinterpret_cast<const half2*>(&raw.x); b = *reinterpret_cast<const half2*>(&raw.y);
-                        }
-                        else if (o.in_mode == 1)
-                        {
-                            const float4 g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A) + e));
-                            const float4 u = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A2) + e));
-                            a = __floats2half2_rn(silu_f32(g.x) * u.x, silu_f32(g.y) * u.y);
-                            b = __floats2half2_rn(silu_f32(g.z) * u.z, silu_f32(g.w) * u.w);
-                        }
-                        else
-                        {
-                            const uint2 gr = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
-                            const uint2 ur = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A2) + e));
-                            const float2 g0 = __half22float2(*reinterpret_cast<const half2*>(&gr.x)), g1 = __half22float2(*reinterpret_cast<const half2*>(&gr.y));
-                            const float2 u0 = __half22float2(*reinterpret_cast<const half2*>(&ur.x)), u1 = __half22float2(*reinterpret_cast<const half2*>(&ur.y));
-                            a = __floats2half2_rn(silu_f32(g0.x) * u0.x, silu_f32(g0.y) * u0.y);
-                            b = __floats2half2_rn(silu_f32(g1.x) * u1.x, silu_f32(g1.y) * u1.y);
-                        }
-                        if (o.suh)
-                        {
-                            const uint2 scb = *reinterpret_cast<const uint2*>(o.suh + kb * 128 + lane * 4);
-                            a = __hmul2(a, *reinterpret_cast<const half2*>(&scb.x));
-                            b = __hmul2(b, *reinterpret_cast<const half2*>(&scb.y));
-                        }
-                        if (o.cached)
-                        {
-                            uint2 st; st.x = *reinterpret_cast<const uint32_t*>(&a); st.y = *reinterpret_cast<const uint32_t*>(&b);
-                            *reinterpret_cast<uint2*>(cache + (size_t) r * o.k + kb * 128 + lane * 4) = st;
-                        }
-                        const float2 fa = __half22float2(a), fb = __half22float2(b);
-                        float ss = fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+                        half2 a[4], b[4];
+                        uint2 scb[4];
                         #pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-                        nmax = fmaxf(nmax, ss);
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const int kb = kb0 + j * CH_XF_WARPS;
+                            a[j] = __floats2half2_rn(0.f, 0.f); b[j] = a[j]; scb[j] = make_uint2(0, 0);
+                            if (kb < KB)
+                            {
+                                const size_t e = (size_t) r * o.k + kb * 128 + lane * 4;
+                                if (o.suh) scb[j] = *reinterpret_cast<const uint2*>(o.suh + kb * 128 + lane * 4);
+                                if (o.in_mode == 0)
+                                {
+                                    const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
+                                    a[j] = *reinterpret_cast<const half2*>(&raw.x); b[j] = *reinterpret_cast<const half2*>(&raw.y);
+                                }
+                                else if (o.in_mode == 1)
+                                {
+                                    const float4 g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A) + e));
+                                    const float4 u = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.A2) + e));
+                                    a[j] = __floats2half2_rn(silu_f32(g.x) * u.x, silu_f32(g.y) * u.y);
+                                    b[j] = __floats2half2_rn(silu_f32(g.z) * u.z, silu_f32(g.w) * u.w);
+                                }
+                                else
+                                {
+                                    const uint2 gr = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
+                                    const uint2 ur = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A2) + e));
+                                    const float2 g0 = __half22float2(*reinterpret_cast<const half2*>(&gr.x)), g1 = __half22float2(*reinterpret_cast<const half2*>(&gr.y));
+                                    const float2 u0 = __half22float2(*reinterpret_cast<const half2*>(&ur.x)), u1 = __half22float2(*reinterpret_cast<const half2*>(&ur.y));
+                                    a[j] = __floats2half2_rn(silu_f32(g0.x) * u0.x, silu_f32(g0.y) * u0.y);
+                                    b[j] = __floats2half2_rn(silu_f32(g1.x) * u1.x, silu_f32(g1.y) * u1.y);
+                                }
+                            }
+                        }
+                        float ss[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const int kb = kb0 + j * CH_XF_WARPS;
+                            if (o.suh)
+                            {
+                                a[j] = __hmul2(a[j], *reinterpret_cast<const half2*>(&scb[j].x));
+                                b[j] = __hmul2(b[j], *reinterpret_cast<const half2*>(&scb[j].y));
+                            }
+                            if (o.cached && kb < KB)
+                            {
+                                uint2 st; st.x = *reinterpret_cast<const uint32_t*>(&a[j]); st.y = *reinterpret_cast<const uint32_t*>(&b[j]);
+                                *reinterpret_cast<uint2*>(cache + (size_t) r * o.k + kb * 128 + lane * 4) = st;
+                            }
+                            const float2 fa = __half22float2(a[j]), fb = __half22float2(b[j]);
+                            ss[j] = fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+                        }
+                        #pragma unroll
+                        for (int d = 16; d > 0; d >>= 1)
+                        {
+                            #pragma unroll
+                            for (int j = 0; j < 4; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], d);
+                        }
+                        nmax = fmaxf(fmaxf(nmax, fmaxf(ss[0], ss[1])), fmaxf(ss[2], ss[3]));
                     }
                     if (lane == 0) atomicMax(&s_norm2[r], __float_as_uint(nmax));
                 }
@@ -480,11 +523,14 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                     // arrive the MMA side observes, the scale the epilogue reads later is ordered before it
                     if (lane == r) s_scale[(cur_op % CH_SCALE_SLOTS) * CH_MR + r] = bnd / (float) I8_QMAX;
                 }
+                CH_STAMP(warp == CH_XF_WARP0 && lane == 0 && c.seq == 0, 60);
             }
             if (turn == xw)
             {
                 // ---- digits of this unit: 128-point Hadamard of the cached block, quantise, two int8 digits x 4 bytes ----
+                CH_STAMP(c.seq == cx.trace_seq && lane == 0, 56);
                 mbar_wait<64>(cx.W_EMPTY(s), ph ^ 1);
+                CH_STAMP(c.seq == cx.trace_seq && lane == 0, 57);
                 uint8_t* dst = smem + cx.L.off_b + s * CH_B_STAGE;
                 int qsum[CH_MR];
                 #pragma unroll
@@ -547,6 +593,7 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(cx.X_FULL(s));
+                CH_STAMP(c.seq == cx.trace_seq && lane == 0, 58);
             }
             if (++turn == CH_XF_WARPS) turn = 0;
             if (++s == S) { s = 0; ph ^= 1; }
@@ -569,14 +616,14 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                 const int m = ops[c.op].m;
                 switch (ops[c.op].K)
                 {
-                    case 1: quad_unit<1>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 2: quad_unit<2>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 3: quad_unit<3>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 4: quad_unit<4>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 5: quad_unit<5>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 6: quad_unit<6>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    case 7: quad_unit<7>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
-                    default: quad_unit<8>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout); break;
+                    case 1: quad_unit<1>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 2: quad_unit<2>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 3: quad_unit<3>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 4: quad_unit<4>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 5: quad_unit<5>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 6: quad_unit<6>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    case 7: quad_unit<7>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    default: quad_unit<8>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
                 }
             }
             if (++s == S) { s = 0; ph ^= 1; }
@@ -654,7 +701,7 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
 
             // who else holds k-segments of this strip?
             const long long gs = o.unit_off + (long long) strip * o.KB;
-            const int c_a = cta_of_unit(U, G, gs), c_b = cta_of_unit(U, G, gs + o.KB - 1);
+            const int c_a = cta_of_unit(U, c.Gs, gs), c_b = cta_of_unit(U, c.Gs, gs + o.KB - 1);
             const bool full = c_a == c_b;
             bool emit = full;
             if (full)
@@ -741,6 +788,7 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
 
     tc_fence_before();
     __syncthreads();
+    CH_STAMP(threadIdx.x == 0, 62);
     if (warp == 0)
     {
         tc_fence_after();

@@ -134,7 +134,12 @@ def launch_count() -> int:
 
 def set_gemm_path(tag: int) -> int:
     """0 = auto, EXL3B_TAG_SIMT, EXL3B_TAG_TC, EXL3B_TAG_TC_I8, EXL3B_TAG_TC_I8_CHAIN.  Returns the previous setting."""
+    global _forced_path
+    _forced_path = int(tag)
     return int(_lib.exl3b_set_gemm_path(int(tag)))
+
+
+_forced_path = 0
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -311,13 +316,13 @@ def exl3_gemm_allreduce(A, B, C, suh, A_had, svh, mcg, mul1) -> int:
 
 
 # Dense exl3_mgemm calls the int8 tensor-core kernel cannot take (other codebooks, or 5..32 rows: the reference's model code
-# fuses k+v and gate+up up to 32 rows, modules/attn.py:603, modules/mlp.py:726) run on the CUDA-core kernels by default.
-# EXL3B_MGEMM_SPLIT=1 instead issues one exact tcgen05 exl3_gemm per matrix (same results as separate calls): that needs the
+# fuses k+v and gate+up up to 32 rows, modules/attn.py:603, modules/mlp.py:726) are issued as one exact tcgen05 exl3_gemm per
+# matrix (tag 200; same results as separate calls, verified against the fused CUDA-core kernels in round 2).  That needs the
 # pointer tables' VALUES on the host, so each table tensor is copied back once and remembered for as long as that tensor
 # object lives and is not modified (weak reference + version counter; never keyed on an address, which the caching allocator
-# reuses).  A table first seen during CUDA-graph capture cannot be copied: such a call keeps the default path.
-# Opt-in until it has run on hardware (round 2).
-_MGEMM_SPLIT = os.environ.get("EXL3B_MGEMM_SPLIT", "0") != "0"
+# reuses).  A table first seen during CUDA-graph capture cannot be copied: such a call runs on the CUDA-core multi-matrix
+# kernels (tag 100), as does everything with EXL3B_MGEMM_SPLIT=0.
+_MGEMM_SPLIT = os.environ.get("EXL3B_MGEMM_SPLIT", "1") != "0"
 _table_cache: dict = {}
 
 
@@ -388,7 +393,7 @@ def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_i
             raise RuntimeError("weights: incorrect number of dimensions, must be 2")
         _dtype(weights, torch.half, "weights")
     cb = _cb(mcg, mul1)
-    if (_MGEMM_SPLIT and indices is None and weights is None and size_n_list is None and min_index < 0 and num_tokens == 1
+    if (_MGEMM_SPLIT and _forced_path in (0, EXL3B_TAG_TC) and indices is None and weights is None and size_n_list is None and min_index < 0 and num_tokens == 1
             and not (cb == 2 and m <= 4) and bszm_in in (1, bszm_out) and m >= 1 and bszm_out >= 1 and k % 128 == 0 and n % 128 == 0):
         tag = _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, k, n, force_num_sms)
         if tag is not None:

@@ -78,9 +78,10 @@ def test_cursor_walk_covers_every_unit_once(specs, num_sms):
             if prev is not None and prev[0] == st:
                 assert g == prev[1] + 1
             prev = (st, g)
-            # the stage-space range of this CTA is [U c / G, U (c + 1) / G)
+            # the stage-space range of this CTA is [U c / Gs, U (c + 1) / Gs), Gs = min(grid, U): no CTA range in between is empty
             U = stage_units[st]
-            assert U * cta // plan.grid <= g < U * (cta + 1) // plan.grid
+            Gs = min(plan.grid, U)
+            assert cta < Gs and U * cta // Gs <= g < U * (cta + 1) // Gs
             # run = this CTA's units inside (op, strip); chunk = <= 96 consecutive units of the run holding seq
             assert rb <= seq < re
             sb, ln = chunk >> 16, chunk & 0xffff
