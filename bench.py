@@ -177,10 +177,11 @@ def run_reference_arm(args, cfg):
 class Token:
     """All quantized linears of one token for one TP rank, with their input/output/scratch buffers."""
 
-    def __init__(self, cfg, tp, rank, dev, seed=1234, fuse=True):
+    def __init__(self, cfg, tp, rank, dev, seed=1234, fuse=True, mode="ops"):
         import torch
         from exllamav3_b200 import ext
         self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
+        self.mode = mode
         self.skip_reduce = False
         self.fused_reduce = False           # row-parallel outputs: one kernel (GEMM + NVLink exchange) instead of GEMM + NCCL
         g = torch.Generator(device=dev); g.manual_seed(seed + rank)
@@ -224,8 +225,64 @@ class Token:
                 self.launches.append(dict(kind="gemm", mt=a, reduce=a["reduce"]))
                 i += 1
 
+        if mode != "ops":
+            self.build_chains(mode)
+
+    def build_chains(self, mode):
+        """
+        The same quantized linears as GEMM chains (ext.GemmChain, one persistent launch per chain) at the granularity of
+          blocks   the reference's C++ block modules: q + k + v | o | gate + up -> silu * mul -> down  (BC_Attention's projections,
+                   libtorch/attention.cpp:286-365; BC_GatedMLP, libtorch/mlp.cpp:14-91) + lm_head: 3 launches per layer
+          layer    one launch per layer (q, k, v -> o -> gate, up -> down as four dependent stages), + lm_head
+          token    the whole token as one launch
+        with the data flow the shapes allow: o reads q's output (stand-in for the attention output, same shape), down reads
+        silu(gate) * up of the gate / up outputs; where the model has non-GEMM ops in between (norms, attention) the chain still
+        carries the DEPENDENCY (the next stage starts only after every output of the previous one is written), its input is the
+        resident buffer of that matrix.  Row-parallel outputs (N > 1) end their chain: the all-reduce follows as its own launch.
+        """
+        ext = self.ext
+        by_layer = {}
+        for mt in self.mats:
+            by_layer.setdefault(mt["layer"], {})[mt["name"]] = mt
+        op = lambda mt, **kw: dict(trellis=mt["tr"], suh=mt["suh"], svh=mt["svh"], y=mt["y"], mul1=True, **kw)
+        self.chain_items = []                 # (GemmChain, matrix whose output is all-reduced afterwards or None)
+        token_ops = []
+        nlayers = max(by_layer) + 1
+        tp_on = self.tp > 1
+        for l in range(nlayers):
+            m_ = by_layer[l]
+            q_in = m_["q"]["x"]
+            qkv = [op(m_["q"], x=q_in), op(m_["k"], x=q_in), op(m_["v"], x=q_in)]
+            o_ = op(m_["o"], x=m_["q"]["y"])
+            gu_in = m_["gate"]["x"]
+            gu = [op(m_["gate"], x=gu_in), op(m_["up"], x=gu_in)]
+            dn = op(m_["down"], gate=m_["gate"]["y"], up=m_["up"]["y"], new_stage=True)
+            if mode == "blocks" or tp_on:
+                self.chain_items += [(ext.GemmChain(qkv), None), (ext.GemmChain([o_]), m_["o"] if m_["o"]["reduce"] else None),
+                                     (ext.GemmChain(gu + [dn]), m_["down"] if m_["down"]["reduce"] else None)]
+            else:
+                ops = [dict(qkv[0], new_stage=l > 0 and mode == "token")] + qkv[1:] + [dict(o_, new_stage=True), dict(gu[0], new_stage=True), gu[1], dn]
+                if mode == "layer":
+                    self.chain_items.append((ext.GemmChain(ops), None))
+                else:
+                    token_ops += ops
+        hd = by_layer[-1]["lm_head"]
+        if mode == "token" and not tp_on:
+            token_ops.append(op(hd, x=hd["x"], new_stage=True))
+            self.chain_items.append((ext.GemmChain(token_ops), None))
+        else:
+            self.chain_items.append((ext.GemmChain([op(hd, x=hd["x"])]), None))
+        self.launches = self.chain_items
+
     def run(self):
         ext, dist = self.ext, None
+        if self.mode != "ops":
+            for ch, red in self.chain_items:
+                ch.run()
+                if red is not None and not self.skip_reduce:
+                    import torch.distributed as dist
+                    dist.all_reduce(red["y"])
+            return
         for ln in self.launches:
             if ln["kind"] == "gemm":
                 mt = ln["mt"]
@@ -359,7 +416,7 @@ def run_gpu_arm(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     from exllamav3_b200 import ext
 
-    tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse)
+    tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse, mode=args.mode)
     if args.fused_allreduce and world > 1:
         from exllamav3_b200 import tp as _tp
         _tp.enable_fused_allreduce(max_elems=4 * cfg["hidden"])
@@ -522,6 +579,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3.1-8b", choices=list(MODELS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mode", default="ops", choices=["ops", "blocks", "layer", "token"],
+                    help="ops: one exl3_gemm / exl3_mgemm launch per projection group (the reference's eager operator granularity); "
+                         "blocks / layer / token: GEMM chains (one persistent launch per block, per layer, per token)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qgemm", action="store_true", help="skip the per-shape qgemm GB/s + prefill tensor-pipe section (N = 1 only)")

@@ -12,12 +12,11 @@
 //     a global counter, and only the warps that PREPARE activations wait for it.  The TMA producer and the decode warps
 //     run on into the next stage's weights (they depend on no activation), so HBM streams through the boundary and the
 //     first operand stages of the next GEMM are decoded before its input exists.
-//   * quads issue their own MMAs.  The 16 decode warps are 4 quads (one warp per TMEM lane quarter).  A quad owns
-//     every 4th unit, decodes it in four rounds of two k-tiles (32 TMEM columns) into its private ring of three operand
-//     slots, and its lead warp issues the round's four MMAs into the quad's private accumulator as soon as the quad's
-//     slot barrier completes: no central MMA warp whose wake-up / issue / commit loop paces all units, four independent
-//     short pipelines instead of two long ones.  Integer accumulation is exact and order-free, so the epilogue just adds
-//     the quads' accumulators.
+//   * the unit pipeline itself is the one of gemm_tc_i8_body.cuh (two decode groups of eight warps, three 128-column TMEM
+//     operand stages, one MMA issuer).  A finer-grained variant -- four quads of four warps issuing their own MMAs from
+//     32-column slots -- was built and measured first (round 2, profiles/r02_chain_notes.md): 1.2 us per unit against 0.5,
+//     because every handshake (mbarrier round trip, tcgen05.wait::st, fence) costs 100-300 cycles of latency regardless of
+//     how little work it guards, so halving the work per round doubled the stall time per weight.
 //   * activation scale without a Hadamard pass.  The quantisation scale only needs an upper bound of max |xh| over
 //     the row; xh is a block-orthonormal transform of x * suh, so max_kb || (x * suh)_kb ||_2 is one -- a plain
 //     reduction pass over the row by three warps (which also applies silu * mul for the gated-MLP input and caches
@@ -26,8 +25,8 @@
 //     (|q| <= 32512 still holds; the scale is up to ~3x larger than the exact maximum, i.e. activations carry ~14.5
 //     instead of 16 bits: rel-RMS contribution 1e-4, tolerance tests in tests/test_chain.py.)
 //
-// Roles (768 threads): warp 0 TMA producer, warps 1-3 activation / digit warps, warps 4-19 decode quads, warps 20-23
-// epilogue.  TMEM: 12 operand slots x 32 columns + 8 accumulators x 16 columns = 512.
+// Roles (768 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 activation / digit warps, warps 4-19 decode (two
+// groups of eight), warps 20-23 epilogue.  TMEM: 3 operand stages x 128 columns + 2 accumulators x 16 columns.
 #include "tc_common.cuh"
 #include "i8_math.cuh"
 #include <mutex>
@@ -38,11 +37,12 @@ namespace exl3b {
 using namespace ptx;
 
 constexpr int CH_THREADS = 768;
-constexpr int CH_XF_WARP0 = 1, CH_XF_WARPS = 3;
-constexpr int CH_DEC_WARP0 = 4;
-constexpr int CH_QUADS = 4, CH_SLOTS = 3, CH_SLOT_COLS = 32;
+constexpr int CH_MMA_WARP = 1;
+constexpr int CH_XF_WARP0 = 2, CH_XF_WARPS = 2;
+constexpr int CH_DEC_WARP0 = 4, CH_DEC_WARPS = 16, CH_DEC_GROUPS = 2;
 constexpr int CH_EPI_WARP0 = 20;
-constexpr int CH_D_COL0 = CH_QUADS * CH_SLOTS * CH_SLOT_COLS;          // 384
+constexpr int CH_A_STAGES = 3, CH_A_STAGE_COLS = 128;
+constexpr int CH_D_COL0 = CH_A_STAGES * CH_A_STAGE_COLS;               // 384
 constexpr int CH_NT = 16, CH_MR = 4;
 constexpr int CH_B_BYTES = 4096, CH_B_STAGE = 4096 + 64;               // digit tile + per-row digit sums
 constexpr int CH_SUB_UNITS = 96;                                       // int32 accumulator safety (see I8_SUB_UNITS)
@@ -63,9 +63,9 @@ struct ChainOp
     int KB, strips;
     int stage;
     int cached;               // x * suh kept in shared memory (m * k * 2 <= cache bytes)
+    int suh_cached;           // suh staged in shared memory by a bulk copy (k * 2 <= suh bytes)
     long long unit_off;       // first unit of this op in its stage's unit space
     float out_scale;
-    int pad_;
 };
 
 struct ChainStage { int op_begin, op_end; int strips_total; int pad_; long long U; };
@@ -74,7 +74,7 @@ struct ChainParams
 {
     const ChainOp* ops; const ChainStage* stages; const CUtensorMap* tmaps;     // device tables (n_inline == 0)
     int n_ops, n_stages, n_inline;
-    int S, w_bytes, cache_bytes;
+    int S, w_bytes, cache_bytes, suh_bytes;
     unsigned int* ctr;        // [n_stages] finished output segments per stage, [n_stages] exit ticket; zero between launches
     float* parts;             // split-K exchange, [2][grid][MR * 128] words, sentinel between launches
     unsigned long long* dbg;
@@ -83,9 +83,9 @@ struct ChainParams
     CUtensorMap tmaps_inline[CH_MAX_INLINE];
 };
 
-struct ChainSmem { int off_b, off_tile, off_bars, off_cache, total; };
+struct ChainSmem { int off_b, off_tile, off_bars, off_cache, off_suh, total; };
 
-__host__ __device__ inline ChainSmem chain_smem(int S, int w_bytes, int cache_bytes)
+__host__ __device__ inline ChainSmem chain_smem(int S, int w_bytes, int cache_bytes, int suh_bytes)
 {
     ChainSmem L;
     L.off_b = S * w_bytes;
@@ -93,7 +93,8 @@ __host__ __device__ inline ChainSmem chain_smem(int S, int w_bytes, int cache_by
     L.off_tile = (L.off_tile + 127) & ~127;
     L.off_bars = L.off_tile + CH_MR * 128 * 4;
     L.off_cache = L.off_bars + 2048;
-    L.total = L.off_cache + cache_bytes;
+    L.off_suh = L.off_cache + cache_bytes;
+    L.total = L.off_suh + suh_bytes;
     return L;
 }
 
@@ -161,52 +162,7 @@ struct Cursor
     }
 };
 
-template <int K>
-__device__ __forceinline__ void ch_load_tiles2(const uint32_t* wst, int tl, int chunk, int prev_lane, int t0, uint32_t (&w)[2][K + 1])
-{
-    #pragma unroll
-    for (int j = 0; j < 2; ++j)
-    {
-        const uint32_t* cp = wst + ((t0 + j) * 8 + tl) * (8 * K) + chunk * K;
-        if constexpr (K % 4 == 0)
-        {
-            #pragma unroll
-            for (int i = 0; i < K; i += 4)
-            {
-                uint4 v = *reinterpret_cast<const uint4*>(cp + i);
-                w[j][1 + i] = v.x; w[j][2 + i] = v.y; w[j][3 + i] = v.z; w[j][4 + i] = v.w;
-            }
-        }
-        else if constexpr (K % 2 == 0)
-        {
-            #pragma unroll
-            for (int i = 0; i < K; i += 2)
-            {
-                uint2 v = *reinterpret_cast<const uint2*>(cp + i);
-                w[j][1 + i] = v.x; w[j][2 + i] = v.y;
-            }
-        }
-        else
-        {
-            #pragma unroll
-            for (int i = 0; i < K; ++i) w[j][1 + i] = cp[i];
-        }
-    }
-    #pragma unroll
-    for (int j = 0; j < 2; ++j)
-        w[j][0] = __shfl_sync(0xffffffffu, w[j][K], prev_lane);
-}
-
 __device__ __forceinline__ float silu_f32(float x) { return x * __fdividef(1.0f, 1.0f + __expf(-x)); }
-
-// Shared state of a decode quad's warp across its units
-struct QuadState
-{
-    int slot, slph;           // operand-slot ring of the quad (one step per round)
-    int dbuf, dph;            // accumulator buffer of the quad (one step per accumulation chunk)
-    uint32_t acc;             // accumulate flag of the next MMA
-    int tsum;                 // lane r < m of the lead warp: digit sum of row r over the chunk so far
-};
 
 struct ChainCtx
 {
@@ -216,16 +172,17 @@ struct ChainCtx
     ChainSmem L;
     uint32_t tmem_base;
     unsigned long long* dbg;
-    int trace_seq;            // bring-up: the unit (CTA-local index) whose rounds are stamped
+    int trace_seq;            // bring-up: the unit (CTA-local index) whose steps are stamped
     __device__ __forceinline__ uint32_t W_FULL(int s) const { return bar0 + 8u * s; }
     __device__ __forceinline__ uint32_t W_EMPTY(int s) const { return bar0 + 8u * (CH_MAX_STAGES + s); }
     __device__ __forceinline__ uint32_t X_FULL(int s) const { return bar0 + 8u * (2 * CH_MAX_STAGES + s); }
-    __device__ __forceinline__ uint32_t SLOT_FULL(int Q, int sl) const { return bar0 + 8u * (3 * CH_MAX_STAGES + Q * CH_SLOTS + sl); }
-    __device__ __forceinline__ uint32_t SLOT_EMPTY(int Q, int sl) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 12 + Q * CH_SLOTS + sl); }
-    __device__ __forceinline__ uint32_t D_FULL(int Q, int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 24 + Q * 2 + b); }
-    __device__ __forceinline__ uint32_t D_EMPTY(int Q, int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 32 + Q * 2 + b); }
+    __device__ __forceinline__ uint32_t A_FULL(int a) const { return bar0 + 8u * (3 * CH_MAX_STAGES + a); }
+    __device__ __forceinline__ uint32_t A_EMPTY(int a) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 4 + a); }
+    __device__ __forceinline__ uint32_t D_FULL(int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 8 + b); }
+    __device__ __forceinline__ uint32_t D_EMPTY(int b) const { return bar0 + 8u * (3 * CH_MAX_STAGES + 10 + b); }
+    __device__ __forceinline__ uint32_t IN_BAR() const { return bar0 + 8u * (3 * CH_MAX_STAGES + 12); }
 };
-constexpr int CH_NUM_BARS = 3 * CH_MAX_STAGES + 40;                    // 88 barriers = 704 B
+constexpr int CH_NUM_BARS = 3 * CH_MAX_STAGES + 13;                    // 61 barriers
 
 #ifdef EXL3B_TC_DEBUG
 #define CH_STAMP(cond, slot) do { if ((cond) && cx.dbg) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__) :: "memory"); cx.dbg[blockIdx.x * 64 + (slot)] = t__; } } while (0)
@@ -233,99 +190,42 @@ constexpr int CH_NUM_BARS = 3 * CH_MAX_STAGES + 40;                    // 88 bar
 #define CH_STAMP(cond, slot) do { } while (0)
 #endif
 
-// One unit (128 k x 128 n weights) of a decode quad: four rounds of two k-tiles.
+// One unit (128 k x 128 n weights) of a decode group (8 warps: two per TMEM lane quarter, alternate k-tiles): the pipeline of
+// gemm_tc_i8_body.cuh -- weight words from the ring stage, four tiles per warp into the unit's 128-column operand stage.
 template <int K>
-__device__ __forceinline__ void quad_unit(const ChainCtx& cx, QuadState& qs, int Q, int q, int lane, int s, int wph,
-                                          bool first, bool last, int m, int* s_tout, [[maybe_unused]] bool trace)
+__device__ __forceinline__ void group_unit(const ChainCtx& cx, int q, int sub, int lane, int s, int sph, int as, int aph,
+                                           [[maybe_unused]] bool trace)
 {
-    [[maybe_unused]] const bool tr_l = trace && q == 0 && lane == 0, tr_n = trace && q == 1 && lane == 0;
     const int tl = strip_tile(q, lane), chunk = lane & 7;
     const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
     const uint32_t lane_base = (uint32_t) (q * 32) << 16;
-    const bool lead = q == 0;
-    mbar_wait<32>(cx.W_FULL(s), wph);
+    [[maybe_unused]] const bool tr = trace && q == 0 && sub == 0 && lane == 0;
+    CH_STAMP(tr, 0);
+    mbar_wait<32>(cx.W_FULL(s), sph);
+    CH_STAMP(tr, 1);
     const uint32_t* wst = reinterpret_cast<const uint32_t*>(cx.smem + s * cx.w_bytes);
-    const uint32_t idesc = idesc_u8s8_s32(128, CH_NT);
-    const uint32_t x_smem = smem_u32(cx.smem + cx.L.off_b + s * CH_B_STAGE);
-    const uint64_t desc0 = smem_desc(x_smem, 128, 4096, 0);
-    const uint32_t desc_hi = (uint32_t) (desc0 >> 32);
-    uint32_t desc_lo = (uint32_t) desc0;
-    int tload = 0;
-    #pragma unroll 1
-    for (int tp = 0; tp < 4; ++tp)
+    uint32_t w[4][K + 1];
+    tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub + 2, sub + 4, sub + 6
+    CH_STAMP(tr, 2);
+    mbar_wait(cx.A_EMPTY(as), aph ^ 1);
+    tc_fence_after();
+    CH_STAMP(tr, 3);
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
     {
-        uint32_t w[2][K + 1];
-        CH_STAMP(tr_l, tp * 8 + 0); CH_STAMP(tr_n, 32 + tp * 6 + 0);
-        ch_load_tiles2<K>(wst, tl, chunk, prev_lane, 2 * tp, w);
-        CH_STAMP(tr_l, tp * 8 + 1); CH_STAMP(tr_n, 32 + tp * 6 + 1);
-        mbar_wait(cx.SLOT_EMPTY(Q, qs.slot), qs.slph ^ 1);
-        tc_fence_after();
-        CH_STAMP(tr_l, tp * 8 + 2); CH_STAMP(tr_n, 32 + tp * 6 + 2);
-        const uint32_t a_col = (uint32_t) ((Q * CH_SLOTS + qs.slot) * CH_SLOT_COLS);
-        #pragma unroll
-        for (int j = 0; j < 2; ++j)
-        {
-            uint32_t o[16];
-            if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
-            tmem_st_32x32b_x16(cx.tmem_base + lane_base + a_col + 16 * j, o);
-        }
-        CH_STAMP(tr_l, tp * 8 + 3); CH_STAMP(tr_n, 32 + tp * 6 + 3);
-        tc_wait_st();
-        CH_STAMP(tr_l, tp * 8 + 4); CH_STAMP(tr_n, 32 + tp * 6 + 4);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0)
-        {
-            mbar_arrive(cx.SLOT_FULL(Q, qs.slot));
-            if (tp == 3) mbar_arrive(cx.W_EMPTY(s));
-        }
-        CH_STAMP(tr_l, tp * 8 + 5); CH_STAMP(tr_n, 32 + tp * 6 + 5);
-        if (lead)
-        {
-            if (tp == 0)
-            {
-                mbar_wait(cx.X_FULL(s), wph);                         // this unit's activation digits are in place
-                if (first)
-                {
-                    mbar_wait(cx.D_EMPTY(Q, qs.dbuf), qs.dph ^ 1);    // the epilogue has drained this accumulator
-                    qs.acc = 0; qs.tsum = 0;
-                }
-                if (lane < m) tload = *reinterpret_cast<const int*>(cx.smem + cx.L.off_b + s * CH_B_STAGE + CH_B_BYTES + 4 * lane);
-                qs.tsum += tload;
-            }
-            mbar_wait(cx.SLOT_FULL(Q, qs.slot), qs.slph);
-            tc_fence_after();
-            CH_STAMP(tr_l, tp * 8 + 6);
-            const bool fin = tp == 3 && last;
-            if (fin)
-            {
-                if (lane < m) s_tout[(Q * 2 + qs.dbuf) * CH_MR + lane] = qs.tsum;     // visible to the epilogue before D_FULL fires
-                __threadfence_block();
-                __syncwarp();
-            }
-            if (elect_one())
-            {
-                const uint32_t d_addr = cx.tmem_base + CH_D_COL0 + (Q * 2 + qs.dbuf) * CH_NT;
-                uint32_t a_addr = cx.tmem_base + a_col;
-                uint32_t dl = desc_lo;
-                #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    mma_i8_ts_step<8, 16>(d_addr, a_addr, dl, desc_hi, idesc, qs.acc);
-                    qs.acc = 1;
-                }
-                tc_commit(cx.SLOT_EMPTY(Q, qs.slot));
-                if (tp == 3) tc_commit(cx.W_EMPTY(s));
-                if (fin) tc_commit(cx.D_FULL(Q, qs.dbuf));
-            }
-            qs.acc = 1;
-            __syncwarp();
-            CH_STAMP(tr_l, tp * 8 + 7);
-            desc_lo += 64;
-            if (fin) { qs.dbuf ^= 1; if (qs.dbuf == 0) qs.dph ^= 1; }
-        }
-        if (++qs.slot == CH_SLOTS) { qs.slot = 0; qs.slph ^= 1; }
+        const int t = sub + 2 * j;
+        uint32_t o[16];
+        if (q & 1) decode16_i8<K, 1>(w[j], o); else decode16_i8<K, 0>(w[j], o);
+        tmem_st_32x32b_x16(cx.tmem_base + lane_base + as * CH_A_STAGE_COLS + 16 * t, o);
     }
+    CH_STAMP(tr, 4);
+    tc_wait_st();
+    CH_STAMP(tr, 5);
+    tc_fence_before();
+    if (sub == 0 && q == 0) mbar_wait(cx.X_FULL(s), sph);              // the group's lead warp vouches for the activation digits
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(cx.A_FULL(as)); mbar_arrive(cx.W_EMPTY(s)); }
+    CH_STAMP(tr, 6);
 }
 
 __device__ __forceinline__ void ch_watchdog(uint32_t& polls, unsigned long long& t0, const char* what, int a, int b)
@@ -339,6 +239,9 @@ __device__ __forceinline__ void ch_watchdog(uint32_t& polls, unsigned long long&
     }
 }
 
+// KSEL = 0: ops of any bitrate (a switch per unit); KSEL = 1..8: every op of the chain has K = KSEL (smaller code: the
+// instruction footprint of all concurrently running roles matters on a kernel this size)
+template <int KSEL>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chain_i8_kernel(const __grid_constant__ ChainParams p)
 {
@@ -349,16 +252,17 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
     const CUtensorMap* tmaps = p.n_inline ? p.tmaps_inline : p.tmaps;
     const int S = p.S;
     ChainCtx cx;
-    cx.smem = smem; cx.S = S; cx.w_bytes = p.w_bytes; cx.L = chain_smem(S, p.w_bytes, p.cache_bytes);
+    cx.smem = smem; cx.S = S; cx.w_bytes = p.w_bytes; cx.L = chain_smem(S, p.w_bytes, p.cache_bytes, p.suh_bytes);
     cx.dbg = p.dbg; cx.trace_seq = 8;
     CH_STAMP(threadIdx.x == 0, 61);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cx.L.off_bars);
     cx.bar0 = smem_u32(bars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cx.L.off_bars + 8 * CH_NUM_BARS);              // +704
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cx.L.off_bars + 8 * CH_NUM_BARS);
     unsigned int* s_norm2 = reinterpret_cast<unsigned int*>(tmem_slot + 4);                                  // [MR] float bits
-    int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                                                     // [4][2][MR]
-    float* s_scale = reinterpret_cast<float*>(tmem_slot + 8 + 32);                                           // [CH_SCALE_SLOTS][MR]
+    int* s_tout = reinterpret_cast<int*>(tmem_slot + 8);                                                     // [2][MR]
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 8 + 8);                                            // [CH_SCALE_SLOTS][MR]
     half* cache = reinterpret_cast<half*>(smem + cx.L.off_cache);
+    half* suh_s = reinterpret_cast<half*>(smem + cx.L.off_suh);
 
     pdl_launch_dependents();
     if (warp == 0)
@@ -366,9 +270,10 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
         for (int i = lane; i < CH_NUM_BARS; i += 32)
         {
             int cnt = 1;
-            if (i >= CH_MAX_STAGES && i < 2 * CH_MAX_STAGES) cnt = 5;                   // W_EMPTY: 4 quad warps + MMA completion
-            else if (i >= 3 * CH_MAX_STAGES && i < 3 * CH_MAX_STAGES + 12) cnt = 4;     // SLOT_FULL: the quad's 4 warps
-            else if (i >= 3 * CH_MAX_STAGES + 32) cnt = 4;                              // D_EMPTY: the 4 epilogue warps
+            if (i >= CH_MAX_STAGES && i < 2 * CH_MAX_STAGES) cnt = CH_DEC_WARPS / CH_DEC_GROUPS + 1;     // W_EMPTY: the group's warps + MMA completion
+            else if (i >= 3 * CH_MAX_STAGES && i < 3 * CH_MAX_STAGES + 4) cnt = CH_DEC_WARPS / CH_DEC_GROUPS;   // A_FULL
+            else if (i >= 3 * CH_MAX_STAGES + 10 && i < 3 * CH_MAX_STAGES + 12) cnt = 4;                 // D_EMPTY: the 4 epilogue warps
+            else if (i == 3 * CH_MAX_STAGES + 12) cnt = 2;                                               // IN_BAR: suh copy + input copy
             mbar_init(cx.bar0 + 8u * i, cnt);
         }
         fence_barrier_init();
@@ -408,23 +313,110 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
         }
         __syncwarp();
     }
+    else if (warp == CH_MMA_WARP)
+    {
+        // =========================== MMA issuer ===========================
+        const uint32_t idesc = idesc_u8s8_s32(128, CH_NT);
+        const uint32_t tb = __shfl_sync(0xffffffffu, cx.tmem_base, 0);
+        const uint64_t desc0 = smem_desc(smem_u32(smem + cx.L.off_b), 128, 4096, 0);
+        const uint32_t desc_hi = (uint32_t) (desc0 >> 32), desc_lo0 = (uint32_t) desc0;
+        uint32_t desc_lo = desc_lo0;
+        Cursor c; c.init(ops, stages, p.n_stages, cta, G);
+        int s = 0, as = 0, aph = 0, dbuf = 0, dphase = 0, tsum = 0, cur_op = -1, m = 0;
+        uint32_t acc = 0;
+        while (c.valid)
+        {
+            int sb, se; c.sub_bounds(sb, se);
+            const bool first = c.seq == sb, last = c.seq == se - 1;
+            if (c.op != cur_op) { cur_op = c.op; m = ops[cur_op].m; }
+            if (first)
+            {
+                mbar_wait(cx.D_EMPTY(dbuf), dphase ^ 1);               // the epilogue has drained this accumulator
+                acc = 0; tsum = 0;
+            }
+            CH_STAMP(lane == 0 && c.seq == cx.trace_seq, 8);
+            // (the unit's activation digits are complete too: the decode group's lead warp waited for X_FULL before it arrived)
+            mbar_wait(cx.A_FULL(as), aph);
+            tc_fence_after();
+            CH_STAMP(lane == 0 && c.seq == cx.trace_seq, 9);
+            if (lane < m) tsum += *reinterpret_cast<const int*>(smem + cx.L.off_b + s * CH_B_STAGE + CH_B_BYTES + 4 * lane);
+            if (last)
+            {
+                if (lane < m) s_tout[dbuf * CH_MR + lane] = tsum;      // visible to the epilogue before D_FULL fires
+                __threadfence_block();
+                __syncwarp();
+            }
+            if (elect_one())
+            {
+                const uint32_t d_addr = tb + CH_D_COL0 + dbuf * CH_NT;
+                uint32_t a_addr = tb + as * CH_A_STAGE_COLS;
+                uint32_t dl = desc_lo;
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    mma_i8_ts_step<8, 16>(d_addr, a_addr, dl, desc_hi, idesc, acc);
+                    acc = 1;
+                }
+                tc_commit(cx.A_EMPTY(as));
+                tc_commit(cx.W_EMPTY(s));
+                if (last) tc_commit(cx.D_FULL(dbuf));
+            }
+            acc = 1;
+            __syncwarp();
+            CH_STAMP(lane == 0 && c.seq == cx.trace_seq, 10);
+            if (last) { dbuf ^= 1; if (dbuf == 0) dphase ^= 1; }
+            desc_lo += CH_B_STAGE >> 4;
+            if (++s == S) { s = 0; desc_lo = desc_lo0; }
+            if (++as == CH_A_STAGES) { as = 0; aph ^= 1; }
+            c.next();
+        }
+        __syncwarp();
+    }
     else if (warp < CH_DEC_WARP0)
     {
         // =========================== activation warps: scale pass per op, digits per unit ===========================
         const int xw = warp - CH_XF_WARP0;
-        auto xf_bar = [] { asm volatile("bar.sync 2, 96;" ::: "memory"); };
+        auto xf_bar = [] { asm volatile("bar.sync 2, %0;" :: "n"(CH_XF_WARPS * 32) : "memory"); };
         pdl_wait();                                                   // external inputs come from the previous kernel
         Cursor c; c.init(ops, stages, p.n_stages, cta, G);
-        int s = 0, ph = 0, cur_op = -1, waited = 0, turn = 0;
+        int s = 0, ph = 0, cur_op = -1, waited = 0, turn = 0, in_ph = 0;
         float inv_scale[CH_MR];
         #pragma unroll
         for (int r = 0; r < CH_MR; ++r) inv_scale[r] = 0.f;
+        // the op's fields live in registers: `ops` is a generic pointer (kernel parameters or global memory), and every
+        // shared-memory store in the loops below would otherwise force a reload of each field (measured: 6 us per scale pass
+        // and 1 us per unit of digits with the fields read through the pointer)
+        struct { const void* A; const void* A2; const half* suh; int m, k, KB, in_mode, cached, suh_cached, stage; } o{};
         while (c.valid)
         {
-            const ChainOp& o = ops[c.op];
             if (c.op != cur_op)
             {
                 cur_op = c.op;
+                {
+                    const ChainOp& g = ops[cur_op];
+                    o.A = g.A; o.A2 = g.A2; o.suh = g.suh; o.m = g.m; o.k = g.k; o.KB = g.KB; o.in_mode = g.in_mode;
+                    o.cached = g.cached; o.suh_cached = g.suh_cached; o.stage = g.stage;
+                }
+                CH_STAMP(warp == CH_XF_WARP0 && lane == 0 && c.seq == 0, 59);
+                const bool bulk_x = o.in_mode == 0 && o.cached;       // input rows by one bulk copy straight into the cache
+                const bool bulk_s = o.suh != nullptr && o.suh_cached;
+                xf_bar();                                             // previous op's cache / suh no longer needed by any digit warp
+                if (warp == CH_XF_WARP0)
+                {
+                    if (lane < CH_MR) s_norm2[lane] = 0u;
+                    // suh does not depend on the previous stage: its copy is in flight while we wait for the stage
+                    if (elect_one())
+                    {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        if (bulk_s)
+                        {
+                            mbar_arrive_expect_tx(cx.IN_BAR(), (uint32_t) (o.k * 2));
+                            bulk_g2s(smem_u32(suh_s), o.suh, (uint32_t) (o.k * 2), cx.IN_BAR(), policy_evict_first());
+                        }
+                        else mbar_arrive(cx.IN_BAR());
+                    }
+                    __syncwarp();
+                }
                 // ---- stage dependency: every output segment of the previous stage has been written ----
                 if (o.stage > waited)
                 {
@@ -432,22 +424,34 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                     {
                         const unsigned int want = (unsigned int) stages[o.stage - 1].strips_total;
                         uint32_t polls = 0; unsigned long long t0 = 0;
-                        while (ld_acquire_gpu_u32(p.ctr + (o.stage - 1)) < want) { __nanosleep(64); ch_watchdog(polls, t0, "stage wait", o.stage, 0); }
+                        while (ld_acquire_gpu_u32(p.ctr + (o.stage - 1)) < want) { __nanosleep(32); ch_watchdog(polls, t0, "stage wait", o.stage, 0); }
                     }
                     __syncwarp();
                     waited = o.stage;
                 }
-                CH_STAMP(warp == CH_XF_WARP0 && lane == 0 && c.seq == 0, 59);
-                xf_bar();                                             // previous op's cache no longer needed by any digit warp
-                if (warp == CH_XF_WARP0 && lane < CH_MR) s_norm2[lane] = 0u;
-                xf_bar();
-                // ---- scale pass: a = input row (silu * mul for the gated input), t = a * suh (fp16, as the reference's
-                //      A_had input), cache t, bound = max over 128-blocks of || t ||_2 ----
+                if (warp == CH_XF_WARP0)
+                {
+                    if (elect_one())
+                    {
+                        if (bulk_x)
+                        {
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            const uint32_t bytes = (uint32_t) ((size_t) o.m * o.k * 2);
+                            mbar_arrive_expect_tx(cx.IN_BAR(), bytes);
+                            bulk_g2s(smem_u32(cache), o.A, bytes, cx.IN_BAR(), policy_evict_first());
+                        }
+                        else mbar_arrive(cx.IN_BAR());
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(cx.IN_BAR(), in_ph);
+                in_ph ^= 1;
+                // ---- scale pass: t = input * suh (fp16, the reference's A_had input), cached; bound = max over 128-blocks of || t ||_2.
+                //      Four blocks per step so that their loads and reductions overlap. ----
                 const int KB = o.KB;
                 for (int r = 0; r < o.m; ++r)
                 {
                     float nmax = 0.f;
-                    // four blocks per step, their loads in flight together (one L2 round trip per step, not per block)
                     for (int kb0 = xw; kb0 < KB; kb0 += 4 * CH_XF_WARPS)
                     {
                         half2 a[4], b[4];
@@ -460,8 +464,14 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
                             if (kb < KB)
                             {
                                 const size_t e = (size_t) r * o.k + kb * 128 + lane * 4;
-                                if (o.suh) scb[j] = *reinterpret_cast<const uint2*>(o.suh + kb * 128 + lane * 4);
-                                if (o.in_mode == 0)
+                                if (o.suh) scb[j] = bulk_s ? *reinterpret_cast<const uint2*>(suh_s + kb * 128 + lane * 4)
+                                                           : *reinterpret_cast<const uint2*>(o.suh + kb * 128 + lane * 4);
+                                if (bulk_x)
+                                {
+                                    const uint2 raw = *reinterpret_cast<const uint2*>(cache + e);
+                                    a[j] = *reinterpret_cast<const half2*>(&raw.x); b[j] = *reinterpret_cast<const half2*>(&raw.y);
+                                }
+                                else if (o.in_mode == 0)
                                 {
                                     const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const half*>(o.A) + e));
                                     a[j] = *reinterpret_cast<const half2*>(&raw.x); b[j] = *reinterpret_cast<const half2*>(&raw.y);
@@ -602,31 +612,34 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
     }
     else if (warp < CH_EPI_WARP0)
     {
-        // =========================== decode quads ===========================
-        const int q = warp & 3, Q = (warp - CH_DEC_WARP0) >> 2;
+        // =========================== decode groups ===========================
+        const int q = warp & 3, wi = (warp - CH_DEC_WARP0) >> 2;         // wi = 0..3
+        const int g = wi & 1, sub = wi >> 1;
         Cursor c; c.init(ops, stages, p.n_stages, cta, G);
-        QuadState qs; qs.slot = 0; qs.slph = 0; qs.dbuf = 0; qs.dph = 0; qs.acc = 0; qs.tsum = 0;
-        int s = 0, ph = 0;
+        int s = 0, ph = 0, as = 0, aph = 0;
         while (c.valid)
         {
-            if ((c.seq & 3) == Q)
+            if ((c.seq & 1) == g)
             {
-                int sb, se; c.sub_bounds(sb, se);
-                const bool first = c.seq - 4 < sb, last = c.seq + 4 >= se;
-                const int m = ops[c.op].m;
-                switch (ops[c.op].K)
+                const bool trace = c.seq == cx.trace_seq;
+                if constexpr (KSEL != 0) group_unit<KSEL>(cx, q, sub, lane, s, ph, as, aph, trace);
+                else
                 {
-                    case 1: quad_unit<1>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 2: quad_unit<2>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 3: quad_unit<3>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 4: quad_unit<4>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 5: quad_unit<5>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 6: quad_unit<6>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    case 7: quad_unit<7>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
-                    default: quad_unit<8>(cx, qs, Q, q, lane, s, ph, first, last, m, s_tout, c.seq == cx.trace_seq); break;
+                    switch (ops[c.op].K)
+                    {
+                        case 1: group_unit<1>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 2: group_unit<2>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 3: group_unit<3>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 4: group_unit<4>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 5: group_unit<5>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 6: group_unit<6>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        case 7: group_unit<7>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                        default: group_unit<8>(cx, q, sub, lane, s, ph, as, aph, trace); break;
+                    }
                 }
             }
             if (++s == S) { s = 0; ph ^= 1; }
+            if (++as == CH_A_STAGES) { as = 0; aph ^= 1; }
             c.next();
         }
     }
@@ -644,59 +657,45 @@ chain_i8_kernel(const __grid_constant__ ChainParams p)
         const float k_inv = __half2float(__ushort_as_half((unsigned short) 0x1eee));
         const float k_bias = __half2float(__ushort_as_half((unsigned short) 0xc931));
         const float c1 = 1534.0f * k_inv + k_bias;
-        int dbuf_bits = 0, dph_bits = 0;                                // per quad: bit Q
+        int dbuf = 0, dphase = 0, cur_op = -1;
+        struct { void* C; const half* svh; long long unit_off; int m, n, KB, c_fp32; float out_scale; } o{};
         Cursor c; c.init(ops, stages, p.n_stages, cta, G);
         while (c.valid)
         {
             const int op = c.op, strip = c.strip, stage = c.stage;
-            const ChainOp& o = ops[op];
+            if (op != cur_op)
+            {
+                cur_op = op;
+                const ChainOp& g = ops[op];
+                o.C = g.C; o.svh = g.svh; o.m = g.m; o.n = g.n; o.KB = g.KB; o.c_fp32 = g.c_fp32; o.unit_off = g.unit_off; o.out_scale = g.out_scale;
+            }
             const int run_begin = c.run_begin, run_end = c.run_end;
             const long long U = stages[stage].U;
-            float* const parts = p.parts + (size_t) (stage & 1) * G * part_stride;
+            float* const parts = p.parts + (size_t) (stage & 1) * DevCtx::I8_PART_CTAS * part_stride;
             float facc[CH_MR];
             #pragma unroll
             for (int r = 0; r < CH_MR; ++r) facc[r] = 0.f;
             for (int sb = run_begin; sb < run_end; sb += CH_SUB_UNITS)
             {
-                const int se = sb + CH_SUB_UNITS < run_end ? sb + CH_SUB_UNITS : run_end;
-                long long dh[CH_MR], dl[CH_MR];
-                int T[CH_MR];
-                #pragma unroll
-                for (int r = 0; r < CH_MR; ++r) { dh[r] = 0; dl[r] = 0; T[r] = 0; }
-                #pragma unroll
-                for (int Q = 0; Q < CH_QUADS; ++Q)
-                {
-                    // does quad Q own a unit of [sb, se)?  first such unit: sb + ((Q - sb) & 3)
-                    if (sb + ((Q - sb) & 3) < se)
-                    {
-                        const int b = (dbuf_bits >> Q) & 1, ph = (dph_bits >> Q) & 1;
-                        mbar_wait<32>(cx.D_FULL(Q, b), ph);
-                        tc_fence_after();
-                        uint32_t rr[16];
-                        tmem_ld_32x32b_x16(cx.tmem_base + lane_base + CH_D_COL0 + (Q * 2 + b) * CH_NT, rr);
-                        tc_wait_ld();
-                        #pragma unroll
-                        for (int r = 0; r < CH_MR; ++r)
-                        {
-                            dh[r] += (int) rr[2 * r]; dl[r] += (int) rr[2 * r + 1];
-                            T[r] += s_tout[(Q * 2 + b) * CH_MR + r];
-                        }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(cx.D_EMPTY(Q, b));
-                        dbuf_bits ^= 1 << Q;
-                        if (b == 1) dph_bits ^= 1 << Q;
-                    }
-                }
+                mbar_wait<32>(cx.D_FULL(dbuf), dphase);
+                tc_fence_after();
+                uint32_t rr[16];
+                tmem_ld_32x32b_x16(cx.tmem_base + lane_base + CH_D_COL0 + dbuf * CH_NT, rr);
+                tc_wait_ld();
                 #pragma unroll
                 for (int r = 0; r < CH_MR; ++r)
                 {
                     if (r < o.m)
                     {
-                        const long long sp = 256ll * dh[r] + dl[r] - 510ll * T[r];
-                        facc[r] += i8_assemble(sp, T[r], s_scale[(op % CH_SCALE_SLOTS) * CH_MR + r], k_inv, c1);
+                        const int T = s_tout[dbuf * CH_MR + r];
+                        const long long sp = i8_centred_sum((int) rr[2 * r], (int) rr[2 * r + 1], T);
+                        facc[r] += i8_assemble(sp, T, s_scale[(op % CH_SCALE_SLOTS) * CH_MR + r], k_inv, c1);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(cx.D_EMPTY(dbuf));
+                dbuf ^= 1; if (dbuf == 0) dphase ^= 1;
             }
 
             // who else holds k-segments of this strip?
@@ -817,7 +816,7 @@ struct Chain
     std::vector<CUtensorMap> tmaps;
     void* d_blob = nullptr;             // device copy: tmaps | ops | stages
     ChainParams p{};
-    int smem_total = 0, grid = 0;
+    int smem_total = 0, grid = 0, ksel = 0;
 };
 
 const char* chain_op_unsupported(int m, int k, int n, int K, int cb, int in_mode)
@@ -838,8 +837,8 @@ static int chain_build(const exl3b_chain_op* in, int n_ops, int num_sms, Chain& 
     EXL3B_CHECK(n_ops <= 4096, EXL3B_ERR_ARG, "exl3_chain: too many ops");
     ch.ops.resize(n_ops);
     ch.stages.clear();
-    int Kmax = 1;
-    size_t cache = 0;
+    int Kmax = 1, Kmin = 9;
+    size_t cache = 0, suhb = 0;
     long long Umax = 0;
     for (int i = 0; i < n_ops; ++i)
     {
@@ -863,34 +862,39 @@ static int chain_build(const exl3b_chain_op* in, int n_ops, int num_sms, Chain& 
         const size_t cb_ = ((size_t) a.m * a.k * 2 + 127) / 128 * 128;
         o.cached = cb_ <= (size_t) CH_CACHE_MAX;
         if (o.cached && cb_ > cache) cache = cb_;
+        o.suh_cached = a.suh != nullptr && (size_t) a.k * 2 <= (size_t) CH_CACHE_MAX && ((uintptr_t) a.suh & 15) == 0;
+        if (o.suh_cached && (size_t) a.k * 2 > suhb) suhb = (size_t) a.k * 2;
+        if (o.cached && o.in_mode == 0 && ((uintptr_t) a.A & 15) != 0) o.cached = 0;      // bulk copy needs 16-byte alignment
+        if (a.K < Kmin) Kmin = a.K;
         st.U += (long long) o.KB * o.strips; st.strips_total += o.strips; st.op_end = i + 1;
         if (a.K > Kmax) Kmax = a.K;
     }
     EXL3B_CHECK(ch.stages.size() <= 255, EXL3B_ERR_UNSUPPORTED, "exl3_chain: more than 255 stages");
     for (const ChainStage& st : ch.stages) if (st.U > Umax) Umax = st.U;
     const int w_bytes = 2048 * Kmax;
-    int S = (220 * 1024 - 128 - CH_MR * 128 * 4 - 2048 - (int) cache) / (w_bytes + CH_B_STAGE);
+    int S = (220 * 1024 - 128 - CH_MR * 128 * 4 - 2048 - (int) cache - (int) suhb) / (w_bytes + CH_B_STAGE);
     if (S > CH_MAX_STAGES) S = CH_MAX_STAGES;
     EXL3B_CHECK(S >= 2, EXL3B_ERR_UNSUPPORTED, "exl3_chain: shared-memory budget exceeded");
-    const ChainSmem L = chain_smem(S, w_bytes, (int) cache);
+    const ChainSmem L = chain_smem(S, w_bytes, (int) cache, (int) suhb);
     EXL3B_CHECK(L.total <= 220 * 1024, EXL3B_ERR_UNSUPPORTED, "exl3_chain: shared-memory budget exceeded");
     int grid = num_sms;
     if (Umax < grid) grid = (int) Umax;
     EXL3B_CHECK(grid <= DevCtx::I8_PART_CTAS, EXL3B_ERR_UNSUPPORTED, "exl3_chain: grid exceeds the split-K exchange buffer");
     ch.p = ChainParams{};
     ch.p.n_ops = n_ops; ch.p.n_stages = (int) ch.stages.size();
-    ch.p.S = S; ch.p.w_bytes = w_bytes; ch.p.cache_bytes = (int) cache;
-    ch.smem_total = L.total; ch.grid = grid;
+    ch.p.S = S; ch.p.w_bytes = w_bytes; ch.p.cache_bytes = (int) cache; ch.p.suh_bytes = (int) suhb;
+    ch.smem_total = L.total; ch.grid = grid; ch.ksel = Kmin == Kmax ? Kmax : 0;
     return 0;
 }
 
-static cudaError_t chain_launch(cudaStream_t stream, int grid, int smem_bytes, const ChainParams& p)
+template <int KSEL>
+static cudaError_t chain_launch_k(cudaStream_t stream, int grid, int smem_bytes, const ChainParams& p)
 {
     static bool attr_set[32] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (!attr_set[dev & 31])
     {
-        cudaError_t e = cudaFuncSetAttribute(chain_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(chain_i8_kernel<KSEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 31] = true;
     }
@@ -900,7 +904,23 @@ static cudaError_t chain_launch(cudaStream_t stream, int grid, int smem_bytes, c
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, chain_i8_kernel, p);
+    return cudaLaunchKernelEx(&cfg, chain_i8_kernel<KSEL>, p);
+}
+
+static cudaError_t chain_launch(cudaStream_t stream, int grid, int smem_bytes, const ChainParams& p, int ksel)
+{
+    switch (ksel)
+    {
+        case 1: return chain_launch_k<1>(stream, grid, smem_bytes, p);
+        case 2: return chain_launch_k<2>(stream, grid, smem_bytes, p);
+        case 3: return chain_launch_k<3>(stream, grid, smem_bytes, p);
+        case 4: return chain_launch_k<4>(stream, grid, smem_bytes, p);
+        case 5: return chain_launch_k<5>(stream, grid, smem_bytes, p);
+        case 6: return chain_launch_k<6>(stream, grid, smem_bytes, p);
+        case 7: return chain_launch_k<7>(stream, grid, smem_bytes, p);
+        case 8: return chain_launch_k<8>(stream, grid, smem_bytes, p);
+        default: return chain_launch_k<0>(stream, grid, smem_bytes, p);
+    }
 }
 
 int chain_plan(const exl3b_chain_op* in, int n_ops, int num_sms, struct exl3b_chain_plan* out)
@@ -969,7 +989,7 @@ int chain_run(cudaStream_t stream, void* chain)
     int dev = -1; EXL3B_CUDA(cudaGetDevice(&dev));
     EXL3B_CHECK(dev == ch->device, EXL3B_ERR_ARG, "exl3_chain_run: chain was created on device %d, current device is %d", ch->device, dev);
     ch->p.dbg = g_tc_dbg;
-    cudaError_t err = chain_launch(stream, ch->grid, ch->smem_total, ch->p);
+    cudaError_t err = chain_launch(stream, ch->grid, ch->smem_total, ch->p, ch->ksel);
     count_launch();
     EXL3B_CUDA(err);
     EXL3B_CUDA(cudaPeekAtLastError());
@@ -1003,7 +1023,7 @@ int launch_gemm_chain(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     { int r = get_weight_tmap(a.B, a.k, a.n, a.K, &p.tmaps_inline[0]); if (r) return r; }
     p.ops_inline[0] = ch.ops[0]; p.stages_inline[0] = ch.stages[0];
     p.n_inline = 1; p.ctr = ctx->chain_ctr; p.parts = ctx->chain_parts; p.dbg = g_tc_dbg;
-    cudaError_t err = chain_launch(stream, ch.grid, ch.smem_total, p);
+    cudaError_t err = chain_launch(stream, ch.grid, ch.smem_total, p, ch.ksel);
     count_launch();
     EXL3B_CUDA(err);
     EXL3B_CUDA(cudaPeekAtLastError());

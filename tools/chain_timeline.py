@@ -40,11 +40,11 @@ d = D[-1]
 ok = (d[:, 0] > 0)
 if ok.any():
     base = d[ok, 0]
-    lab = ["top", "LDS", "SLOT_EMPTY", "decode+STTM", "wait::st", "arrived", "SLOT_FULL", "MMA issued"]
-    for tp in range(4):
-        print("  lead warp round", tp, {l: med(d[ok, tp * 8 + j] - base) for j, l in enumerate(lab)})
-    okn = d[:, 32] > 0
-    for tp in range(4):
-        print("  warp q=1 round", tp, {l: med(d[okn, 32 + tp * 6 + j] - d[okn, 32]) for j, l in enumerate(lab[:6])})
+    lab = ["top", "W_FULL", "LDS+SHFL", "A_EMPTY", "decode+STTM issued", "wait::st", "arrived"]
+    print("  decode warp (group lead), unit 8:", {l: med(d[ok, j] - base) for j, l in enumerate(lab)}, " absolute start:", med(base - t0_last) if False else "")
+    okm = d[:, 8] > 0
+    print("  mma warp, unit 8 (rel. decode top):", {"loop top": med(d[okm & ok, 8] - d[okm & ok, 0]), "A_FULL": med(d[okm & ok, 9] - d[okm & ok, 0]), "issued+committed": med(d[okm & ok, 10] - d[okm & ok, 0])})
     okx = d[:, 56] > 0
-    print("  digit warp, unit 8:", {"W_EMPTY": med(d[okx, 57] - d[okx, 56]), "digits+arrive": med(d[okx, 58] - d[okx, 56]), "start vs lead top": med(d[okx & ok, 56] - d[okx & ok, 0])})
+    print("  digit warp, unit 8:", {"W_EMPTY": med(d[okx, 57] - d[okx, 56]), "digits+arrive": med(d[okx, 58] - d[okx, 56]), "start vs decode top": med(d[okx & ok, 56] - d[okx & ok, 0])})
+    e = d[ok]
+    print("  absolute (vs this launch's entry): decode unit 8 top", med(e[:, 0] - e[:, 61]), " scale pass end", med(e[:, 60] - e[:, 61]), " exit", med(e[:, 62] - e[:, 61]))

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+set -u
+out=gpurun_out/r02_call5
+mkdir -p "$out"
+timeout 600 python -m pytest tests/test_chain.py -q -m gpu -x > "$out/chain_tests.log" 2>&1; echo "chain tests rc=$?" | tee "$out/summary.txt"
+tail -n 12 "$out/chain_tests.log"
+for shp in "4096 14336 4" "4096 4096 4"; do
+  EXL3B_LIBRARY=$PWD/exllamav3_b200/libexl3b200_dbg.so timeout 300 python tools/chain_timeline.py $shp > "$out/timeline_$(echo $shp | tr ' ' '_').log" 2>&1
+  echo "timeline $shp rc=$?" | tee -a "$out/summary.txt"
+  cat "$out/timeline_$(echo $shp | tr ' ' '_').log"
+done
+timeout 900 python tools/chain_bench.py > "$out/chain_bench.log" 2>&1; echo "chain bench rc=$?" | tee -a "$out/summary.txt"
+tail -n 14 "$out/chain_bench.log" | cut -c1-400
+timeout 600 python -m pytest tests -q -m gpu -x --deselect tests/test_chain.py > "$out/gpu_suite.log" 2>&1; echo "suite rc=$?" | tee -a "$out/summary.txt"
+tail -n 5 "$out/gpu_suite.log"
