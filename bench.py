@@ -102,11 +102,12 @@ class ClockSampler:
 # CPU arm (oracle port of the reference's torch dequant + matmul path)
 # ---------------------------------------------------------------------------------------------------------------------
 
-def cpu_path_time(cfg, budget_s=20.0):
+def cpu_path_time(cfg, budget_s=None):
     """
     Reference semantics: W = get_weight_tensor() (decode -> H128 left -> *suh -> H128 right -> *svh, torch fp32
     matmuls with the 128x128 Hadamard, modules/quant/exl3.py:227-237 + quantize.py:340-357), then x @ W in fp32.
-    Sample: as many whole matrices of layer 0 (q, k, v, o, gate, up, down order) as fit the time budget.
+    Sample: ALL seven matrices of layer 0 (q, k, v, o, gate, up, down), always the same work (budget_s = None), so that two
+    runs differ only by the host they ran on; a budget cuts the sample short (used by nothing but quick local checks).
     Returns (weights_per_second, cores, sample_description, (y, name, k, n) of the first matrix for validation).
     """
     import ctypes, numpy as np, torch
@@ -136,7 +137,7 @@ def cpu_path_time(cfg, budget_s=20.0):
         t_total += dt; done_w += k * n; names.append(name)
         if first is None:
             first = (y.numpy().copy(), name, k, n, K)
-        if t_total > budget_s:
+        if budget_s is not None and t_total > budget_s:
             break
     return done_w / t_total, cores, f"layer-0 matrices {'+'.join(names)} ({done_w / 1e6:.1f} M weights, {t_total:.1f} s)", first
 
@@ -150,12 +151,14 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wps, cores, sample, _ = cpu_path_time(cfg, budget_s=10.0)   # warm-up / page-in
+    wps, cores, sample, _ = cpu_path_time(cfg, budget_s=5.0)    # warm-up / page-in
     vals = []
-    for _ in range(max(1, args.steps)):
-        wps, cores, sample, _ = cpu_path_time(cfg, budget_s=min(20.0, 120.0 / max(1, args.steps)))
+    evals = max(1, min(args.steps, 3))                          # each evaluation is the whole fixed sample (~10-30 s of CPU work)
+    for _ in range(evals):
+        wps, cores, sample, _ = cpu_path_time(cfg)
         vals.append(wps / weights_per_token(cfg))
     v = statistics.median(vals)
+    sample += f"; median of {evals} evaluations"
     line = {
         "impl": "reference", "metric": "decode tok/s Llama-3.1-8B 4.0bpw b=1 (qgemm path)", "value": v, "unit": "tok/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
@@ -341,6 +344,54 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
                                    "GBps": round(b / best / 1e3, 1), "frac_of_hbm_peak": round(b / best / 1e3 / hbm_peak, 3),
                                    "distinct_weight_MB": round(len(mats) * mt["k"] * mt["n"] * mt["K"] / 8 / 1e6)}
         del g
+    # batch 8 / 32 decode (BASELINE config 3) on the default path: exact tcgen05 kernel, one launch per call
+    out["decode_batch"] = {}
+    for name in ("q", "gate", "down"):
+        mats = by_name[name]
+        for m in (8, 32):
+            mt0 = mats[0]
+            xb = torch.randn((m, mt0["k"]), device=tok.dev).half(); xhb = torch.empty_like(xb)
+            yb = torch.empty((m, mt0["n"]), dtype=torch.float if mt0["c_fp32"] else torch.half, device=tok.dev)
+            tag = [0]
+            def runb():
+                for mt in mats:
+                    tag[0] = ext.exl3_gemm(xb, mt["tr"], yb, mt["suh"], xhb, mt["svh"], -1, False, True, 0)
+            with torch.cuda.stream(stream):
+                runb()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                runb()
+            best = None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream); g.replay(); g.replay(); e1.record(stream)
+                e1.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / (2 * len(mats))
+                best = us if best is None else min(best, us)
+            b = alg_bytes(m, mt0["k"], mt0["n"], mt0["K"], mt0["c_fp32"])
+            out["decode_batch"][f"{name}_m{m}"] = {"us_per_launch": round(best, 2), "GBps": round(b / best / 1e3, 1),
+                                                    "frac_of_hbm_peak": round(b / best / 1e3 / hbm_peak, 3), "tag": int(tag[0])}
+            del g
+    # the reference's own CUDA kernels (unmodified sources compiled for sm_100a, oracle/_ref) on this GPU in this run, its default
+    # configuration, same shapes and method (graph replay over >= 512 MB of rotated weight copies): the bar the kernels are held to
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "exl3_ref_ext.so")
+    if os.path.exists(ref_so) and not os.environ.get("EXL3B_BENCH_NO_REF_CUDA"):
+        try:
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                env = dict(os.environ); env.update(REF_BENCH_SHAPES="decode", REF_BENCH_OUT=td, EXLLAMAV3_TUNE_CACHE=os.path.join(td, "tune"))
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "bench_ref_gpu.py"), "int8"], env=env,
+                                   capture_output=True, text=True, timeout=300)
+                res = json.load(open(os.path.join(td, "ref_bench_int8.json")))
+            out["reference_cuda"] = {"what": "unmodified reference kernels (exllamav3_ext, default settings: its int8 GEMV for mul1 at m <= 2, "
+                                             "mma.sync kernels otherwise), same GPU, same run, outside every timed region",
+                                     "shapes": {f"{d['shape']} m={d['m']}": {"us": round(d["us"], 2), "GBps": round(d["gbps"], 1)} for d in res}}
+        except Exception as e:
+            out["reference_cuda"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    else:
+        out["reference_cuda"] = {"unavailable": "oracle/_ref/exl3_ref_ext.so not present (built only where the reference checkout exists)"}
     # prefill: batch 32 x seq 2048 rows through the reference-facing linear (rows > 144 -> reconstruct + dense GEMM)
     peaks = {}
     try:
@@ -417,10 +468,14 @@ def run_gpu_arm(args, cfg):
     from exllamav3_b200 import ext
 
     tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse, mode=args.mode)
-    if args.fused_allreduce and world > 1:
+    if world > 1 and not args.nccl_allreduce and args.mode == "ops" and not args.tp_shapes:
         from exllamav3_b200 import tp as _tp
-        _tp.enable_fused_allreduce(max_elems=4 * cfg["hidden"])
-        tok.fused_reduce = True
+        try:
+            _tp.enable_fused_allreduce(max_elems=4 * cfg["hidden"])
+            tok.fused_reduce = True
+        except Exception as e:                  # no peer access / IPC: every rank fails alike (collective setup), NCCL it is
+            if rank == 0:
+                print(f"# fused all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
     if args.tp_shapes:
         # single-GPU dry run of ONE rank's shard of a TP-N token (kernel shapes only, no collective): not a bench result
         tok.skip_reduce = True
@@ -497,6 +552,19 @@ def run_gpu_arm(args, cfg):
         for _ in range(3):
             e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps     # events bracket the loop; host round trips are inside
+    # the same without the CUDA graph: one Python -> ctypes -> C ABI call per launch, what the reference's eager module path does
+    e2e_eager_ms = None
+    if graph is not None:
+        def e2e_eager_step():
+            tok.first_x.copy_(hx, non_blocking=True)
+            tok.run()
+            hlogits.copy_(tok.logits, non_blocking=True)
+            stream.synchronize()
+        n_eager = max(3, min(args.steps, 50))
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                e2e_eager_step()
+        e2e_eager_ms = timed(e2e_eager_step, n_eager) / n_eager
 
     peak, peak_src = read_peaks()
     achieved = tok.alg_bytes / (ms_per_step * 1e-3) / 1e9          # per rank (each rank streams its own shard)
@@ -506,7 +574,7 @@ def run_gpu_arm(args, cfg):
     cpu_baseline = None
     check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        wps, cores, sample, first = cpu_path_time(cfg, budget_s=args.cpu_budget)
+        wps, cores, sample, first = cpu_path_time(cfg, budget_s=args.cpu_budget if args.cpu_budget > 0 else None)
         cpu_baseline = {"value": wps / weights_per_token(cfg), "unit": "tok/s", "cores": cores, "kind": "port",
                         "sample": sample}
         # validate the GPU path on the same matrix the CPU arm just computed (oracle as checker only)
@@ -554,7 +622,10 @@ def run_gpu_arm(args, cfg):
                                  "launch scaled from the ncu --set full capture in profiles/ (measured/algorithmic = 1.0006)"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "tok/s", "h2d_bytes_per_step": hx.numel() * 2,
-                    "d2h_bytes_per_step": hlogits.numel() * hlogits.element_size()},
+                    "d2h_bytes_per_step": hlogits.numel() * hlogits.element_size(),
+                    "eager_value": (1000.0 / e2e_eager_ms) if e2e_eager_ms else None,
+                    "note": "value: CUDA-graph replay of the token between the host copies; eager_value: the same with one "
+                            "Python -> ctypes -> C-ABI call per launch (no graph), as the reference's eager module path issues them"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "check": check,
@@ -574,7 +645,7 @@ def run_gpu_arm(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400, help="timed tokens (default: >= 1 s of timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3.1-8b", choices=list(MODELS))
@@ -585,11 +656,12 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qgemm", action="store_true", help="skip the per-shape qgemm GB/s + prefill tensor-pipe section (N = 1 only)")
-    ap.add_argument("--fused-allreduce", action="store_true",
-                    help="N > 1: row-parallel outputs through exl3_gemm_allreduce (one kernel) instead of exl3_gemm + NCCL; "
-                         "opt-in until verified on hardware")
+    ap.add_argument("--fused-allreduce", action="store_true", help="(default for N > 1 since round 2; kept for old command lines)")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: row-parallel outputs as exl3_gemm + NCCL all-reduce (what the reference issues) instead of the one-kernel "
+                         "exl3_gemm_allreduce")
     ap.add_argument("--tp-shapes", type=int, default=0, help="debug: run rank 0's shard shapes of a TP-N token on one GPU without the all-reduce")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds; 0 = the fixed sample (all of layer 0)")
     args = ap.parse_args()
     cfg = MODELS[args.model]
     if args.impl == "reference":

@@ -222,20 +222,45 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     }
     if (warp >= TC_XF_WARP0 && warp < TC_EPI_WARP0)
     {
-        pdl_wait();                                       // A is produced by the previous kernel
         const int nw = TC_EPI_WARP0 - TC_XF_WARP0;       // 18 warps
         if constexpr (MR <= 4)
         {
-            for (int task = warp - TC_XF_WARP0; task < p.m * KB; task += nw)
+            // Two tasks (row, k-block) per step with both loads in flight together, and the suh blocks of the first step fetched
+            // BEFORE griddepcontrol.wait: suh is a weight (it does not depend on the previous kernel) and usually comes from
+            // DRAM, the activations come from L2 -- one DRAM latency and one L2 latency less on every launch's critical path.
+            const int T = p.m * KB, w0 = warp - TC_XF_WARP0;
+            uint2 sc0 = make_uint2(0, 0), sc1 = make_uint2(0, 0);
+            if (suh)
             {
-                const int r = task / KB, kb = task % KB;
+                if (w0 < T) sc0 = *reinterpret_cast<const uint2*>(suh + (w0 % KB) * 128 + lane * 4);
+                if (w0 + nw < T) sc1 = *reinterpret_cast<const uint2*>(suh + ((w0 + nw) % KB) * 128 + lane * 4);
+            }
+            if constexpr (!ROUTED) pdl_wait();            // A is produced by the previous kernel (ROUTED waited at the top)
+            for (int task = w0; task < T; task += 2 * nw)
+            {
+                const int ta = task, tb = task + nw;
+                const int ra = ta / KB, ka = ta % KB, rb = tb / KB, kb_ = tb % KB;
+                if (task != w0 && suh)
+                {
+                    sc0 = *reinterpret_cast<const uint2*>(suh + ka * 128 + lane * 4);
+                    if (tb < T) sc1 = *reinterpret_cast<const uint2*>(suh + kb_ * 128 + lane * 4);
+                }
+                const uint2 raw0 = *reinterpret_cast<const uint2*>(A_raw + (size_t) ra * p.k + ka * 128 + lane * 4);
+                uint2 raw1 = make_uint2(0, 0);
+                if (tb < T) raw1 = *reinterpret_cast<const uint2*>(A_raw + (size_t) rb * p.k + kb_ * 128 + lane * 4);
                 float v[4];
-                xh_block(r, kb, v);
-                xh_publish(r, kb, v);
+                xh_finish(raw0, sc0, v);
+                xh_publish(ra, ka, v);
+                if (tb < T)
+                {
+                    xh_finish(raw1, sc1, v);
+                    xh_publish(rb, kb_, v);
+                }
             }
         }
         else
         {
+            pdl_wait();                                   // A is produced by the previous kernel
             // up to 8 rows: one k-block of ALL rows per step, the rows' loads in flight together (one L2 round trip per step
             // instead of one per row)
             for (int kb = warp - TC_XF_WARP0; kb < KB; kb += nw)

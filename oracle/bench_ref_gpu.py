@@ -19,6 +19,9 @@ SHAPES = [("q/o", 4096, 4096, 4, 1), ("k/v", 4096, 1024, 4, 1), ("gate/up", 4096
 
 def main(mode):
     import torch
+    global SHAPES
+    if os.environ.get("REF_BENCH_SHAPES") == "decode":       # bench.py's same-run leg: the Llama decode shapes only
+        SHAPES = SHAPES[:7]
     dev = torch.device("cuda:0")
     if mode == "ours":
         from exllamav3_b200 import ext as e
@@ -72,8 +75,9 @@ def main(mode):
         print(mode, res[-1], flush=True)
         del Bs
         torch.cuda.empty_cache()
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"ref_bench_{mode}.json"), "w"), indent=1)
+    out_dir = os.environ.get("REF_BENCH_OUT") or os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    json.dump(res, open(os.path.join(out_dir, f"ref_bench_{mode}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

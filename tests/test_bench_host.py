@@ -105,6 +105,7 @@ def test_qgemm_section_control_flow(monkeypatch):
         def synchronize(self): pass
 
     calls = []
+    monkeypatch.setenv("EXL3B_BENCH_NO_REF_CUDA", "1")       # the same-run reference-kernel leg spawns a GPU process
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "graph", lambda g, stream=None: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
@@ -116,9 +117,11 @@ def test_qgemm_section_control_flow(monkeypatch):
     assert set(out["decode_hbm"]) == {"q", "k", "v", "o", "gate", "up", "down", "lm_head"}
     q = out["decode_hbm"]["q"]
     assert (q["k"], q["n"], q["K"]) == (256, 256, 4) and q["us_per_launch"] > 0 and q["GBps"] > 0 and q["frac_of_hbm_peak"] >= 0
-    # every shape: one warm-up pass + one captured pass over its layer instances
-    assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"]           # q and o share the shape
-    assert calls.count(("gemm", 256, 640)) == 2
+    # every shape: one warm-up pass + one captured pass over its layer instances; the batch-8 / 32 leg adds the same for q twice
+    assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"] + 2 * 2 * TINY["layers"]    # q and o share the shape
+    assert set(out["decode_batch"]) == {"q_m8", "q_m32", "gate_m8", "gate_m32", "down_m8", "down_m32"}
+    assert out["decode_batch"]["q_m8"]["tag"] == 210 and "reference_cuda" in out
+    assert calls.count(("gemm", 256, 640)) >= 2
     pre = [c for c in calls if c[0] == "prefill"]
     assert {(c[1], c[2]) for c in pre} == {((65536, 256), 256), ((16384, 256), 512)} and len(pre) == 2 * 7
     for v in out["prefill_tensor"].values():

@@ -6,7 +6,7 @@ from exllamav3_b200 import ext
 k, n, K, m = [int(v) for v in sys.argv[1:5]]
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 4
 if len(sys.argv) > 6:
-    ext.set_gemm_path(ext.EXL3B_TAG_TC if sys.argv[6] == "tc" else ext.EXL3B_TAG_SIMT)
+    ext.set_gemm_path({"tc": ext.EXL3B_TAG_TC, "simt": ext.EXL3B_TAG_SIMT, "i8": ext.EXL3B_TAG_TC_I8, "chain": ext.EXL3B_TAG_TC_I8_CHAIN}[sys.argv[6]])
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(0)
 Bs = [torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16) for _ in range(iters)]
