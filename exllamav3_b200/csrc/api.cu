@@ -96,7 +96,7 @@ int ensure_xh_tiled(DevCtx* ctx, size_t bytes_per_slot)
 
 }  // namespace exl3b
 
-namespace exl3b { void tc_set_debug_buffer(unsigned long long* d); void tc_set_knob(int k); }
+namespace exl3b { void tc_set_debug_buffer(unsigned long long* d); void tc_set_knob(int k); void hgemm_set_pair_mode(int mode); }
 using namespace exl3b;
 
 extern "C" {
@@ -112,6 +112,8 @@ int exl3b_set_gemm_path(int tag) { return g_force_path.exchange(tag); }
 // bring-up aid (not in the public header): per-CTA %globaltimer stamps of the tcgen05 kernel, 16 x u64 per CTA
 void exl3b_debug_tc_timeline(void* dev_buf) { exl3b::tc_set_debug_buffer((unsigned long long*) dev_buf); }
 void exl3b_debug_tc_knob(int knob) { exl3b::tc_set_knob(knob); }
+// measurement aid (not in the public header): dense GEMM tile mode, 0 = auto (CTA pairs above 128 rows), 1 = single CTA, 2 = pairs
+void exl3b_debug_hgemm_pair(int mode) { exl3b::hgemm_set_pair_mode(mode); }
 
 int exl3b_num_sms(int device)
 {

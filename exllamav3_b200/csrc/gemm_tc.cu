@@ -562,12 +562,22 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
     return 0;
 }
 
+// The in-kernel input transform (two warps, per UNIT) pays off while a CTA sees few units: at 5..8 rows it costs ~1 us per
+// unit, so beyond ~8 units per CTA the separate had_tiled launch + tile loads is faster (measured, profiles/r02_bench_n1.json:
+// 4096 x 14336 at 8 rows 44 us fused against 28 us at 32 rows through the tiled path).
+static bool tc_fused_x(int m, int k, int n, int num_sms)
+{
+    if (m <= 4) return true;
+    if (m > 8) return false;
+    return (long long) (k / 128) * (n / 128) <= 8ll * num_sms;
+}
+
 // launch geometry of one pass (m <= 256 rows), also behind exl3b_gemm_plan
 int plan_gemm_tc(int m, int k, int n, int K, int num_sms, int max_ctas, TcPlan* pl)
 {
     EXL3B_CHECK(m >= 1 && m <= 256, EXL3B_ERR_ARG, "plan_gemm_tc: one pass handles 1..256 rows");
     const int NT = (m + 15) / 16 * 16;
-    const bool fused_x = m <= 8;
+    const bool fused_x = tc_fused_x(m, k, n, num_sms);
     // all of TMEM: the operand-stage loop (decode -> tcgen05.st -> MMA -> commit -> decode) has ~1.3 us of latency;
     // the number of 64-column A stages in flight is what hides it (measured: 3 stages = 450 ns per unit floor)
     pl->tmem_cols = 512;

@@ -36,14 +36,19 @@ def timeit():
     for (m, k, n) in [(2048, 4096, 4096), (8192, 4096, 4096), (65536, 4096, 4096), (8192, 4096, 14336), (8192, 14336, 4096)]:
         a = torch.randn((m, k), device=dev).half(); b = torch.randn((k, n), device=dev).half()
         c = torch.empty((m, n), dtype=torch.half, device=dev)
-        for _ in range(3): ext.hgemm(a, b, c)
-        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         it = 10
-        e0.record()
-        for _ in range(it): ext.hgemm(a, b, c)
-        e1.record(); e1.synchronize()
-        ms = e0.elapsed_time(e1) / it
+        res = {}
+        for mode, name in ((1, "single_cta"), (2, "cta_pair")):
+            ext.lib.exl3b_debug_hgemm_pair(mode)
+            for _ in range(3): ext.hgemm(a, b, c)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(it): ext.hgemm(a, b, c)
+            e1.record(); e1.synchronize()
+            res[name] = e0.elapsed_time(e1) / it
+        ext.lib.exl3b_debug_hgemm_pair(0)
+        ms = min(res.values())
         tf = 2.0 * m * k * n / ms / 1e9
         for _ in range(3): torch.matmul(a, b, out=c)
         torch.cuda.synchronize()
@@ -51,7 +56,9 @@ def timeit():
         for _ in range(it): torch.matmul(a, b, out=c)
         e1.record(); e1.synchronize()
         ms2 = e0.elapsed_time(e1) / it
-        print(json.dumps(dict(m=m, k=k, n=n, ms=ms, tflops=tf, cublas_ms=ms2, cublas_tflops=2.0 * m * k * n / ms2 / 1e9)), flush=True)
+        print(json.dumps(dict(m=m, k=k, n=n, ms=ms, tflops=tf, ms_single_cta=res["single_cta"], ms_cta_pair=res["cta_pair"],
+                              tflops_cta_pair=2.0 * m * k * n / res["cta_pair"] / 1e9, cublas_ms=ms2, cublas_tflops=2.0 * m * k * n / ms2 / 1e9,
+                              pair_vs_cublas=ms2 / res["cta_pair"])), flush=True)
 
 
 if __name__ == "__main__":
