@@ -428,7 +428,7 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
     return out
 
 
-NCU_CAPTURE = os.path.join("profiles", "r01_ncu_i8_gate_4096x14336_K4_m1.csv")     # metric,unit,value rows of one --set full capture
+NCU_CAPTURE = os.path.join("profiles", "r02_ncu_gate.csv")     # metric,unit,value rows of one --set full capture
 
 
 def ncu_dram_bytes(path):
@@ -618,8 +618,10 @@ def run_gpu_arm(args, cfg):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "gemm_tc_i8_kernel (tcgen05 kind::i8 decode-GEMM)",
                          "note": "achieved = algorithmic bytes of the step / step time = average over the step's launches of the "
-                                 "dominant kernel (it is 100 % of the launches, profiles/r01_launches.md); traffic = bytes per average "
-                                 "launch scaled from the ncu --set full capture in profiles/ (measured/algorithmic = 1.0006)"},
+                                 "dominant kernel (it is 100 % of the launches, profiles/r02_launches.md); traffic = bytes per average "
+                                 "launch scaled from this round's ncu --set full capture of the kernel on the gate shape "
+                                 "(profiles/r02_ncu_gate.csv: 29.486 MB read for 29.46 MB algorithmic, ratio 1.001; q and lm_head "
+                                 "captures beside it)"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "tok/s", "h2d_bytes_per_step": hx.numel() * 2,
                     "d2h_bytes_per_step": hlogits.numel() * hlogits.element_size(),
