@@ -27,6 +27,7 @@
 #include "decode.cuh"
 #include "epilogue.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <unordered_map>
 #include <mutex>
 
@@ -569,7 +570,13 @@ static bool tc_fused_x(int m, int k, int n, int num_sms)
 {
     if (m <= 4) return true;
     if (m > 8) return false;
-    return (long long) (k / 128) * (n / 128) <= 8ll * num_sms;
+    static int per_cta = -1;                      // units per CTA up to which 5..8 rows keep the in-kernel transform
+    if (per_cta < 0)
+    {
+        const char* e = getenv("EXL3B_FUSED_X_UNITS");
+        per_cta = e ? atoi(e) : 2;
+    }
+    return (long long) (k / 128) * (n / 128) <= (long long) per_cta * num_sms;
 }
 
 // launch geometry of one pass (m <= 256 rows), also behind exl3b_gemm_plan
