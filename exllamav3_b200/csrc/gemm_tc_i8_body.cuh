@@ -49,6 +49,18 @@ using namespace ptx;
 #define EXL3B_I8_K4_BRANCHFREE 0
 #endif
 
+// Round-2 experiments on the unit pipeline (each a second build of the library, timed in the same run; profiles/r02_notes.md):
+//   EXL3B_I8_PREFETCH    the decode warps load the NEXT unit's weight words (LDS + shuffles) right after the last decode of the
+//                        current one, i.e. during tcgen05.wait::st, if that ring stage has already landed (non-blocking probe)
+//   EXL3B_I8_HALF_STAGE  an operand stage is released in two halves (after the 8th and the 16th MMA of its unit): the next writer's
+//                        first tiles start ~180 cycles earlier
+#ifndef EXL3B_I8_PREFETCH
+#define EXL3B_I8_PREFETCH 0
+#endif
+#ifndef EXL3B_I8_HALF_STAGE
+#define EXL3B_I8_HALF_STAGE 0
+#endif
+
 constexpr int I8_MAX_M = 8;                                    // rows per launch: kernel instantiated for MR = 4 and MR = 8 rows
 constexpr int I8_A_STAGE_COLS = 128;
 constexpr int I8_A_STAGES = 3;
@@ -128,7 +140,8 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     auto A_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 4 + s); };
     auto D_FULL = [&](int s) { return bar0 + 8u * (3 * S + 8 + s); };
     auto D_EMPTY = [&](int s) { return bar0 + 8u * (3 * S + 10 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 12));
+    [[maybe_unused]] auto A_EMPTY_HI = [&](int s) { return bar0 + 8u * (3 * S + 12 + s); };      // second half of an operand stage (EXL3B_I8_HALF_STAGE)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_bars + 8 * (3 * TC_MAX_STAGES + 16));
     unsigned int* s_absmax = reinterpret_cast<unsigned int*>(tmem_slot + 4);      // [MR] float bits, >= 0
     int* s_tout = reinterpret_cast<int*>(tmem_slot + 12);                           // [2][MR] digit sums per D buffer
     [[maybe_unused]] volatile unsigned int* s_ar = reinterpret_cast<volatile unsigned int*>(tmem_slot + 28);   // AR: epoch of this launch
@@ -160,7 +173,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     {
         // one barrier per lane and round instead of ~60 serial initialisations by one thread (0.3 us of every launch)
         for (int s = lane; s < S; s += 32) { mbar_init(W_FULL(s), 1); mbar_init(X_FULL(s), 1); mbar_init(W_EMPTY(s), TC_DEC_WARPS / I8_DEC_GROUPS + 1); }
-        if (lane < 4) { mbar_init(A_FULL(lane), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(lane), 1); }
+        if (lane < 4) { mbar_init(A_FULL(lane), TC_DEC_WARPS / I8_DEC_GROUPS); mbar_init(A_EMPTY(lane), 1); mbar_init(A_EMPTY_HI(lane), 1); }
         else if (lane < 6) { mbar_init(D_FULL(lane - 4), 1); mbar_init(D_EMPTY(lane - 4), 4); }
         else if (lane < 6 + MR) s_absmax[lane - 6] = 0u;
         fence_barrier_init();
@@ -390,9 +403,16 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                     {
                         mma_i8_ts_step<8, 16>(d_addr, a_addr, dl, desc_hi, idesc, acc);
                         acc = 1;
+#if EXL3B_I8_HALF_STAGE
+                        if (j == 7) tc_commit(A_EMPTY(as));              // columns 0..63 (tiles 0..3) are free again
+#endif
                     }
                 }
+#if EXL3B_I8_HALF_STAGE
+                tc_commit(A_EMPTY_HI(as));
+#else
                 tc_commit(A_EMPTY(as));
+#endif
                 tc_commit(W_EMPTY(s));
                 if (sub_left == 0) tc_commit(D_FULL(dbuf));
             }
@@ -495,6 +515,8 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
         const int prev_lane = (lane & ~7) | ((lane + 7) & 7);
         const uint32_t lane_base = (uint32_t) (q * 32) << 16;
         int s = g % S, sph = 0, as = g % I8_A_STAGES, aph = 0;
+        [[maybe_unused]] bool have_w = false;                                  // EXL3B_I8_PREFETCH: w already holds this unit's words
+        uint32_t w[4][K + 1];
         for (int u = g; u < n_units; u += I8_DEC_GROUPS)
         {
 #ifdef EXL3B_TC_DEBUG
@@ -505,13 +527,17 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
 #define I8_STAMP(i)
 #endif
             I8_STAMP(0);
-            I8_WAITCNT(wf_a, W_FULL(s), sph);
-            mbar_wait<32>(W_FULL(s), sph);
-            I8_STAMP(1);
-            if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
-            const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
-            uint32_t w[4][K + 1];
-            tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub+2, sub+4, sub+6
+#if EXL3B_I8_PREFETCH
+            if (!have_w)
+#endif
+            {
+                I8_WAITCNT(wf_a, W_FULL(s), sph);
+                mbar_wait<32>(W_FULL(s), sph);
+                I8_STAMP(1);
+                if (u == 0 && warp == TC_DEC_WARP0 && lane == 0) stamp(3);
+                const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem + s * L.w_bytes);
+                tc_load_tiles4<K>(wst, tl, chunk, prev_lane, sub, 2, w);           // tiles sub, sub+2, sub+4, sub+6
+            }
             I8_STAMP(2);
             I8_WAITCNT(wf_b, A_EMPTY(as), aph ^ 1);
             mbar_wait(A_EMPTY(as), aph ^ 1);
@@ -520,6 +546,9 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
             #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
+#if EXL3B_I8_HALF_STAGE
+                if (j == 2) { mbar_wait(A_EMPTY_HI(as), aph ^ 1); tc_fence_after(); }     // tiles 4..7 live in the stage's second half
+#endif
                 const int t = sub + 2 * j;
                 uint32_t o[16];
                 if (KNOB & 1)
@@ -536,6 +565,24 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                 else if (o[0] == 0x12345678u && o[15] == 0x9abcdef0u) p.counters[0] = 1;
             }
             I8_STAMP(4);
+#if EXL3B_I8_PREFETCH
+            {
+                // the next unit of this group: ring stage s + 2.  If its weights have landed, fetch its words now: the LDS /
+                // shuffle latency then overlaps the drain of the tcgen05.st above instead of opening the next unit.
+                have_w = false;
+                if (u + I8_DEC_GROUPS < n_units)
+                {
+                    int s2 = s + I8_DEC_GROUPS, sph2 = sph;
+                    if (s2 >= S) { s2 -= S; sph2 ^= 1; }
+                    if (__all_sync(0xffffffffu, mbar_test_wait(W_FULL(s2), sph2)))
+                    {
+                        const uint32_t* wst2 = reinterpret_cast<const uint32_t*>(smem + s2 * L.w_bytes);
+                        tc_load_tiles4<K>(wst2, tl, chunk, prev_lane, sub, 2, w);
+                        have_w = true;
+                    }
+                }
+            }
+#endif
             tc_wait_st();
             I8_STAMP(5);
             tc_fence_before();
