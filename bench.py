@@ -75,7 +75,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.index),
                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -528,12 +528,18 @@ def run_gpu_arm(args, cfg):
             ms = float(t.item())
         return ms
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(3, args.warmup)):
-            step()
+    # clocks are sampled from the warm-up on (same load as the timed steps), so that even a short timed region has samples
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                     # nvidia-smi start-up
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            step()
+        if args.steps < 200:                # short timed region: keep the GPU under the same load a little longer first
+            for _ in range(200):
+                step()
+    stream.synchronize()
     ms = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps

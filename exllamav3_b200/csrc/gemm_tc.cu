@@ -563,9 +563,9 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
     return 0;
 }
 
-// The in-kernel input transform (two warps, per UNIT) pays off while a CTA sees few units: at 5..8 rows it costs ~1 us per
-// unit, so beyond ~8 units per CTA the separate had_tiled launch + tile loads is faster (measured, profiles/r02_bench_n1.json:
-// 4096 x 14336 at 8 rows 44 us fused against 28 us at 32 rows through the tiled path).
+// In-kernel input transform (two warps, per unit) or the separate had_tiled launch + tile loads for 5..8 rows: measured the same to
+// 0.1 us on 4096 x 4096 and 4096 x 14336 (EXL3B_FUSED_X_UNITS = units per CTA up to which the in-kernel transform is used; A/B in
+// profiles/r02_notes.md 5), so the transform is not what makes 5..8 rows slower than 32 on the wide shapes (44 vs 28 us on gate).
 static bool tc_fused_x(int m, int k, int n, int num_sms)
 {
     if (m <= 4) return true;
@@ -574,7 +574,7 @@ static bool tc_fused_x(int m, int k, int n, int num_sms)
     if (per_cta < 0)
     {
         const char* e = getenv("EXL3B_FUSED_X_UNITS");
-        per_cta = e ? atoi(e) : 2;
+        per_cta = e ? atoi(e) : 8;
     }
     return (long long) (k / 128) * (n / 128) <= (long long) per_cta * num_sms;
 }
