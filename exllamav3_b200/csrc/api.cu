@@ -7,6 +7,7 @@
 #include <string>
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 
 namespace exl3b {
 

@@ -563,20 +563,21 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
     return 0;
 }
 
-// In-kernel input transform (two warps, per unit) or the separate had_tiled launch + tile loads for 5..8 rows: measured the same to
-// 0.1 us on 4096 x 4096 and 4096 x 14336 (EXL3B_FUSED_X_UNITS = units per CTA up to which the in-kernel transform is used; A/B in
-// profiles/r02_notes.md 5), so the transform is not what makes 5..8 rows slower than 32 on the wide shapes (44 vs 28 us on gate).
+// In-kernel input transform (two warps, per unit) or the separate had_tiled launch + tile loads?  Measured (round 2,
+// profiles/r02_notes.md 5; us per call, in-kernel vs tiled): 5 rows 16.0 vs 13.7 (4096 x 4096), 33.4 vs 22.8 (4096 x 14336),
+// 34.8 vs 24.2 (14336 x 4096); 8 rows 19.3 vs 13.7, 44.5 vs 22.9, 46.1 vs 25.9 -- the two transform warps pace the kernel from five
+// rows on (one 128-point Hadamard per row and unit), so the in-kernel transform is kept for <= EXL3B_FUSED_X_ROWS (default 4) rows.
 static bool tc_fused_x(int m, int k, int n, int num_sms)
 {
-    if (m <= 4) return true;
-    if (m > 8) return false;
-    static int per_cta = -1;                      // units per CTA up to which 5..8 rows keep the in-kernel transform
-    if (per_cta < 0)
+    (void) k; (void) n; (void) num_sms;
+    static int max_rows = -1;
+    if (max_rows < 0)
     {
-        const char* e = getenv("EXL3B_FUSED_X_UNITS");
-        per_cta = e ? atoi(e) : 8;
+        const char* e = getenv("EXL3B_FUSED_X_ROWS");
+        max_rows = e ? atoi(e) : 4;
+        if (max_rows > 8) max_rows = 8;
     }
-    return (long long) (k / 128) * (n / 128) <= (long long) per_cta * num_sms;
+    return m <= max_rows;
 }
 
 // launch geometry of one pass (m <= 256 rows), also behind exl3b_gemm_plan
@@ -622,7 +623,7 @@ int launch_gemm_tc(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
         { int r = plan_gemm_tc(m, a.k, a.n, a.K, ctx->num_sms, a.max_ctas, &pl); if (r) return r; }
         const int NT = pl.rows;
         const int slot = ctx->next_slot();
-        const bool fused_x = m <= 8;
+        const bool fused_x = tc_fused_x(m, a.k, a.n, ctx->num_sms);
         uint8_t* xh_tiled = nullptr;
         if (!fused_x)
         {
