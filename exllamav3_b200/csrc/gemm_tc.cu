@@ -566,7 +566,9 @@ static int launch_had_tiled(cudaStream_t stream, const half* A, uint8_t* out, co
 // In-kernel input transform (two warps, per unit) or the separate had_tiled launch + tile loads?  Measured (round 2,
 // profiles/r02_notes.md 5; us per call, in-kernel vs tiled): 5 rows 16.0 vs 13.7 (4096 x 4096), 33.4 vs 22.8 (4096 x 14336),
 // 34.8 vs 24.2 (14336 x 4096); 8 rows 19.3 vs 13.7, 44.5 vs 22.9, 46.1 vs 25.9 -- the two transform warps pace the kernel from five
-// rows on (one 128-point Hadamard per row and unit), so the in-kernel transform is kept for <= EXL3B_FUSED_X_ROWS (default 4) rows.
+// rows on (one 128-point Hadamard per row and unit).  At 1..4 rows (3INST codebook) the two are equal on 4096 x 4096 (13.5 us) and the
+// tiled path is ahead on 4096 x 14336 (24.4 vs 25.0 us at 1 row, 24.4 vs 30.3 at 4 rows), so the tiled path is the default for every
+// row count; EXL3B_FUSED_X_ROWS=r (<= 8) brings the in-kernel transform back for up to r rows.
 static bool tc_fused_x(int m, int k, int n, int num_sms)
 {
     (void) k; (void) n; (void) num_sms;
@@ -574,7 +576,7 @@ static bool tc_fused_x(int m, int k, int n, int num_sms)
     if (max_rows < 0)
     {
         const char* e = getenv("EXL3B_FUSED_X_ROWS");
-        max_rows = e ? atoi(e) : 4;
+        max_rows = e ? atoi(e) : 0;
         if (max_rows > 8) max_rows = 8;
     }
     return m <= max_rows;
