@@ -392,6 +392,27 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
             out["reference_cuda"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     else:
         out["reference_cuda"] = {"unavailable": "oracle/_ref/exl3_ref_ext.so not present (built only where the reference checkout exists)"}
+    # weight materialisation kernels of the prefill sibling (reconstruct / reconstruct_had): write-dominated, K/8 + 2 bytes per weight
+    out["reconstruct"] = {}
+    for (k, n) in ((cfg["hidden"], cfg["q"]), (cfg["hidden"], cfg["inter"])):
+        mt = next(t for t in tok.mats if t["k"] == k and t["n"] == n)
+        w = torch.empty((k, n), dtype=torch.half, device=tok.dev)
+        for nm, fn in (("reconstruct", lambda: ext.reconstruct(w, mt["tr"], mt["K"], False, True)),
+                       ("reconstruct_had", lambda: ext.reconstruct_had_slice(w, mt["tr"], mt["suh"], mt["svh"], mt["K"], False, True, 0))):
+            with torch.cuda.stream(stream):
+                fn(); fn()
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(10):
+                    fn()
+                e1.record(stream)
+            e1.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / 10
+            b = k * n * (mt["K"] / 8 + 2)
+            out["reconstruct"][f"{nm}_{k}x{n}"] = {"us": round(us, 2), "GBps": round(b / us / 1e3, 1), "frac_of_hbm_peak": round(b / us / 1e3 / hbm_peak, 3)}
+        del w
     # prefill: batch 32 x seq 2048 rows through the reference-facing linear (rows > 144 -> reconstruct + dense GEMM)
     peaks = {}
     try:

@@ -111,6 +111,8 @@ def test_qgemm_section_control_flow(monkeypatch):
     monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
     monkeypatch.setattr(torch.cuda, "Event", Ev)
     monkeypatch.setattr(ext, "exl3_gemm", lambda *a: calls.append(("gemm", a[0].shape[-1], a[2].shape[-1])) or 210)
+    monkeypatch.setattr(ext, "reconstruct", lambda *a: calls.append(("rec",)))
+    monkeypatch.setattr(ext, "reconstruct_had_slice", lambda *a: calls.append(("rec_had",)))
     monkeypatch.setattr(QLinear, "forward", lambda self, x, params, out_dtype=None: calls.append(("prefill", tuple(x.shape), self.out_features)) or x)
     tok = bench.Token(TINY, 1, 0, torch.device("cpu"))
     out = bench.qgemm_section(tok, TINY, Stream(), 6576.1)
@@ -121,6 +123,7 @@ def test_qgemm_section_control_flow(monkeypatch):
     assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"] + 2 * 2 * TINY["layers"]    # q and o share the shape
     assert set(out["decode_batch"]) == {"q_m8", "q_m32", "gate_m8", "gate_m32", "down_m8", "down_m32"}
     assert out["decode_batch"]["q_m8"]["tag"] == 210 and "reference_cuda" in out
+    assert set(out["reconstruct"]) == {"reconstruct_256x256", "reconstruct_had_256x256", "reconstruct_256x512", "reconstruct_had_256x512"}
     assert calls.count(("gemm", 256, 640)) >= 2
     pre = [c for c in calls if c[0] == "prefill"]
     assert {(c[1], c[2]) for c in pre} == {((65536, 256), 256), ((16384, 256), 512)} and len(pre) == 2 * 7

@@ -195,6 +195,34 @@ def test_hgemm(cuda):
     assert rel_err(cfull[:, 128:256].cpu().numpy(), ref)[0] <= 2e-3 and float(cfull[:, :128].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_hgemm_single_cta_and_cta_pair_tiles(cuda, mode):
+    """Both tile modes of the dense tcgen05 GEMM on the same inputs: 1 = one CTA per 128 x 256 tile, 2 = a CTA pair
+    (tcgen05.mma.cta_group::2) per 256 x 256 tile -- ragged m / n / k, a single 128-row tile (second CTA of the pair all out of
+    range), strided C, both output types; against an fp64 product of the fp16 operands (the reference's hgemm is cuBLAS, hgemm.cu:19-102)."""
+    from exllamav3_b200 import ext
+    rng = np.random.default_rng(mode)
+    ext.lib.exl3b_debug_hgemm_pair(mode)
+    try:
+        for (m, k, n) in ((300, 512, 256), (129, 72, 264), (1, 128, 128), (513, 200, 520), (1024, 1024, 768)):
+            a = rng.standard_normal((m, k)).astype(np.float16); b = rng.standard_normal((k, n)).astype(np.float16)
+            ref = a.astype(np.float64) @ b.astype(np.float64)
+            for dt in (torch.half, torch.float):
+                c = torch.full((m, n), float("nan"), dtype=dt, device=cuda)
+                ext.hgemm(T(a, cuda), T(b, cuda), c)
+                torch.cuda.synchronize()
+                assert not torch.isnan(c.float()).any(), (mode, m, k, n, dt)
+                mx, rms = rel_err(c.cpu().numpy(), ref)
+                assert mx <= (2e-3 if dt == torch.half else 1e-4), (mode, m, k, n, dt, mx)
+        a = rng.standard_normal((260, 128)).astype(np.float16); b = rng.standard_normal((128, 128)).astype(np.float16)
+        cfull = torch.zeros((260, 384), dtype=torch.half, device=cuda)
+        ext.hgemm(T(a, cuda), T(b, cuda), cfull[:, 128:256])
+        assert rel_err(cfull[:, 128:256].cpu().numpy(), a.astype(np.float64) @ b.astype(np.float64))[0] <= 2e-3
+        assert float(cfull[:, :128].abs().max()) == 0.0 and float(cfull[:, 256:].abs().max()) == 0.0
+    finally:
+        ext.lib.exl3b_debug_hgemm_pair(0)
+
+
 def test_linear_exl3_kernel_vs_reconstruct_path(cuda):
     # the reference's own pin of this path: tests/test_qgemm.py:31-53 (rtol = atol = 0.05), m list from there
     from exllamav3_b200 import QLinear
