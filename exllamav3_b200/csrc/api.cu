@@ -4,6 +4,8 @@
 #include "epilogue.cuh"
 #include "tc_common.cuh"
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 #include <string>
 #include <atomic>
 #include <cstring>
@@ -115,6 +117,7 @@ void exl3b_debug_tc_timeline(void* dev_buf) { exl3b::tc_set_debug_buffer((unsign
 void exl3b_debug_tc_knob(int knob) { exl3b::tc_set_knob(knob); }
 // measurement aid (not in the public header): dense GEMM tile mode, 0 = auto (CTA pairs above 128 rows), 1 = single CTA, 2 = pairs
 void exl3b_debug_hgemm_pair(int mode) { exl3b::hgemm_set_pair_mode(mode); }
+void exl3b_debug_reconstruct_had(int mode) { exl3b::reconstruct_had_set_mode(mode); }
 
 int exl3b_num_sms(int device)
 {
@@ -179,6 +182,9 @@ int exl3b_reconstruct_had(void* stream, void* unpacked, const void* packed, cons
                 "reconstruct slice exceeds packed tensor bounds");
     EXL3B_CHECK(unpacked && packed && suh && svh, EXL3B_ERR_ARG, "reconstruct_had: null tensor");
     DevCtx* ctx; r = get_ctx(&ctx); if (r) return r;
+    if (reconstruct_had_tc_enabled())
+        return launch_reconstruct_had_tc((cudaStream_t) stream, (half*) unpacked, (const uint16_t*) packed, (const half*) suh,
+                                         (const half*) svh, k, n_out, packed_tiles_n, K, cb, n_offset, ctx->num_sms);
     return launch_reconstruct_had((cudaStream_t) stream, (half*) unpacked, (const uint16_t*) packed,
                                   (const half*) suh, (const half*) svh, k, n_out, packed_tiles_n, K, cb, n_offset);
 }
@@ -315,6 +321,27 @@ int exl3b_tp_debug_inject(void* stream, int src_rank, const void* partial, int64
 int exl3b_tp_debug_peek(int buffer_rank, int slot, int src_rank, void* host_out, int64_t count) { return tp_debug_peek(buffer_rank, slot, src_rank, host_out, (long long) count); }
 int64_t exl3b_tp_debug_epoch(void) { return tp_debug_epoch(); }
 
+// Host copies of size_n_list tensors (device int32) the caller vouches for: the fan-out launch geometry (CTA groups, row pitch)
+// depends on the widths, and the reference's operator only hands over the device tensor.  Keyed by the device address.
+static std::mutex g_widths_mu;
+static std::unordered_map<const void*, std::vector<int32_t>> g_widths;
+
+int exl3b_register_widths(const int32_t* size_n_list, const int32_t* host_widths, int count)
+{
+    EXL3B_CHECK(size_n_list, EXL3B_ERR_ARG, "register_widths: null device pointer");
+    EXL3B_CHECK(count >= 0 && (count == 0 || host_widths), EXL3B_ERR_ARG, "register_widths: bad host list");
+    std::lock_guard<std::mutex> lock(g_widths_mu);
+    if (count == 0) g_widths.erase(size_n_list);
+    else g_widths[size_n_list] = std::vector<int32_t>(host_widths, host_widths + count);
+    return 0;
+}
+
+int exl3b_plan_fanout(int k, const int32_t* host_widths, int count, int num_sms, int32_t* cta0)
+{
+    EXL3B_CHECK(host_widths && cta0 && num_sms >= 1, EXL3B_ERR_ARG, "plan_fanout: bad argument");
+    return plan_fanout_groups(k, host_widths, count, num_sms, cta0);
+}
+
 int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, const uint64_t* suh_ptrs, void* A_had,
                 const uint64_t* svh_ptrs, const int64_t* indices, int num_indices, const void* weights,
                 int bszm_in, int bszm_out, int m, int k, int n, int K, int cb, int c_fp32,
@@ -350,6 +377,13 @@ int exl3b_mgemm(void* stream, const void* A, const uint64_t* B_ptrs, void* C, co
     a.bszm_in = bszm_in; a.bszm_out = bszm_out; a.m = m; a.k = k; a.n = n; a.K = K; a.cb = cb;
     a.c_fp32 = c_fp32 != 0; a.min_index = min_index; a.max_index = max_index; a.num_tokens = num_tokens;
     a.size_n_list = size_n_list; a.c_ptrs = c_ptrs; a.num_c_ptrs = num_c_ptrs;
+    std::vector<int32_t> widths;                    // copy: the registry may change under another thread
+    if (size_n_list)
+    {
+        std::lock_guard<std::mutex> lock(g_widths_mu);
+        auto it = g_widths.find(size_n_list);
+        if (it != g_widths.end() && (int) it->second.size() == num_c_ptrs) { widths = it->second; a.size_n_host = widths.data(); }
+    }
     const int path = g_force_path.load();
     if ((path == EXL3B_TAG_TC_I8 || path == EXL3B_TAG_TC_I8_ROUTED || (path == 0 && m <= 4)) && mgemm_tc_i8_supported(ctx, a))
         return launch_mgemm_tc_i8((cudaStream_t) stream, ctx, a);

@@ -83,6 +83,11 @@ int launch_reconstruct(cudaStream_t stream, half* unpacked, const uint16_t* pack
                        int packed_tiles_n, int K, int cb, int64_t n_offset);
 int launch_reconstruct_had(cudaStream_t stream, half* unpacked, const uint16_t* packed, const half* suh,
                            const half* svh, int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset);
+// tensor-core variant (reconstruct_tc.cu): both Hadamards as tcgen05 GEMMs; the default unless EXL3B_RECONSTRUCT_HAD=simt
+bool reconstruct_had_tc_enabled();
+void reconstruct_had_set_mode(int mode);
+int launch_reconstruct_had_tc(cudaStream_t stream, half* unpacked, const uint16_t* packed, const half* suh, const half* svh,
+                              int k, int n_out, int packed_tiles_n, int K, int cb, int64_t n_offset, int num_sms);
 
 struct GemmArgs
 {
@@ -142,7 +147,11 @@ struct MGemmArgs
     int bszm_in, bszm_out, m, k, n, K, cb; bool c_fp32;
     int min_index, max_index, num_tokens;
     const int32_t* size_n_list; const uint64_t* c_ptrs; int num_c_ptrs;
+    const int32_t* size_n_host;          // host copy of size_n_list if the caller registered one (exl3b_register_widths), else null
 };
+// fan-out launches (per-matrix widths) on the tcgen05 int8 path: CTA group boundaries proportional to the matrices' unit counts
+// (host + tests: the partition the kernel is given); returns the grid size, 0 if the shapes do not fit
+int plan_fanout_groups(int k, const int32_t* widths, int mats, int num_sms, int* cta0 /* mats + 1 */);
 int launch_mgemm(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a);
 
 // persistent multi-GEMM kernel (chain_i8.cu)

@@ -103,11 +103,45 @@ int launch_gemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const GemmArgs& a)
     return EXL3B_TAG_TC_I8;
 }
 
+// Fan-out partition: matrix j gets a share of the persistent grid proportional to its units (k/128 x n_j/128), at least one CTA
+// and at most one CTA per unit; the shares are handed out left to right from what is left, so they always sum to the grid.
+int plan_fanout_groups(int k, const int32_t* widths, int mats, int num_sms, int* cta0)
+{
+    if (mats < 1 || mats > TC_RAG_MAX_MATS || mats > num_sms) return 0;
+    long long U[TC_RAG_MAX_MATS], Utot = 0;
+    for (int j = 0; j < mats; ++j)
+    {
+        if (widths[j] < 128 || widths[j] % 128) return 0;
+        U[j] = (long long) (k / 128) * (widths[j] / 128); Utot += U[j];
+    }
+    int grid = num_sms; if (grid > Utot) grid = (int) Utot;
+    long long Urem = Utot; int Grem = grid; cta0[0] = 0;
+    for (int j = 0; j < mats; ++j)
+    {
+        const int after = mats - 1 - j;                                        // matrices still to be served: one CTA each at least
+        long long g = (Grem * U[j] + Urem / 2) / Urem;
+        if (g < 1) g = 1;
+        if (g > Grem - after) g = Grem - after;
+        if (g > U[j]) g = U[j];
+        cta0[j + 1] = cta0[j] + (int) g;
+        Grem -= (int) g; Urem -= U[j];
+    }
+    return cta0[mats];
+}
+
 bool mgemm_tc_i8_supported(const DevCtx* ctx, const MGemmArgs& a)
 {
-    // dense case only: one output per matrix, shared or per-matrix input, no routing / weighting / ragged widths
+    // dense case only: one output per matrix, shared or per-matrix input, no routing / weighting; per-matrix widths (fan-out) only
+    // when the caller registered a host copy of the width list (the launch geometry depends on it)
     if (a.cb != 2 || !i8_rows_ok(a.m, a.k)) return false;
-    if (a.indices || a.weights || a.size_n_list || a.min_index >= 0 || a.num_tokens != 1) return false;
+    if (a.indices || a.weights || a.min_index >= 0 || a.num_tokens != 1) return false;
+    if (a.size_n_list)
+    {
+        if (!a.size_n_host || !a.c_ptrs || a.k < 128 || a.k % 128) return false;
+        if (!(a.bszm_in == 1 || a.bszm_in == a.bszm_out)) return false;
+        int cta0[TC_RAG_MAX_MATS + 1];
+        return plan_fanout_groups(a.k, a.size_n_host, a.bszm_out, ctx->num_sms, cta0) > 0;
+    }
     if (a.bszm_out < 1 || !(a.bszm_in == 1 || a.bszm_in == a.bszm_out)) return false;
     if (a.bszm_out > ctx->num_sms || a.bszm_out > DevCtx::TMAP_SLOTS) return false;
     if (a.k < 128 || a.n < 128 || a.k % 128 || a.n % 128) return false;
@@ -122,7 +156,7 @@ int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
 {
     const int mats = a.bszm_out;
     CUtensorMap tmap;
-    { int r = get_weight_tmap(ctx->ws, a.k, a.n, a.K, &tmap); if (r) return r; }     // template: address patched per CTA
+    { int r = get_weight_tmap(ctx->ws, a.k, a.size_n_list ? 128 : a.n, a.K, &tmap); if (r) return r; }     // template: address patched per CTA (unused by fan-out launches)
     const int slot = ctx->next_slot();
     TcParams p{};
     p.C = a.C; p.m = a.m; p.k = a.k; p.n = a.n; p.NT = I8_NT; p.c_fp32 = a.c_fp32;
@@ -149,7 +183,15 @@ int launch_mgemm_tc_i8(cudaStream_t stream, DevCtx* ctx, const MGemmArgs& a)
     int gpm = ctx->num_sms / mats;
     if (gpm > U) gpm = (int) U;
     p.g_per_mat = gpm;
-    const int grid = gpm * mats;
+    int grid = gpm * mats;
+    if (a.size_n_list)
+    {
+        // fan-out: per-matrix widths and output pointers (exl3_gemm_kernel.cuh:172-181); the weights arrive as row copies, no tensor map
+        p.rag = 1; p.c_ptrs = a.c_ptrs;
+        grid = plan_fanout_groups(a.k, a.size_n_host, mats, ctx->num_sms, p.rag_cta0);
+        EXL3B_CHECK(grid > 0, EXL3B_ERR_UNSUPPORTED, "exl3_mgemm (i8): fan-out widths not supported");
+        for (int j = 0; j < mats; ++j) p.rag_n[j] = a.size_n_host[j];
+    }
     cudaError_t err = cudaSuccess;
     switch (a.K)
     {

@@ -111,10 +111,20 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     const bool multi = p.num_mats > 0;
     float* const parts = p.parts;                    // split-K exchange buffer, one slot of MR x 128 floats per CTA of the grid
     int cta0 = 0;                                    // first CTA of this matrix's group
+    int n_loc = p.n;                                 // output width of this CTA's matrix
     [[maybe_unused]] float routed_scale = 1.f;
     if (multi)
     {
-        G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G;
+        if (p.rag)
+        {
+            // fan-out: CTA groups proportional to the matrices' unit counts (host-computed boundaries)
+            #pragma unroll
+            for (int j = 1; j < TC_RAG_MAX_MATS; ++j) if (j < p.num_mats && (int) blockIdx.x >= p.rag_cta0[j]) mat = j;
+            #pragma unroll
+            for (int j = 0; j < TC_RAG_MAX_MATS; ++j) if (j == mat) { cta0 = p.rag_cta0[j]; G = p.rag_cta0[j + 1] - cta0; n_loc = p.rag_n[j]; }
+            cta = blockIdx.x - cta0;
+        }
+        else { G = p.g_per_mat; mat = blockIdx.x / G; cta = blockIdx.x - mat * G; cta0 = mat * G; }
         const int slot = mat;                        // inputs / outputs are per slot, the pointer tables per matrix
         if constexpr (ROUTED)
         {
@@ -128,7 +138,8 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
             if (route->has_weights) routed_scale = __half2float(route->tab->weight[slot]);
         }
         suh = reinterpret_cast<const half*>(p.suh_ptrs[mat]); svh = reinterpret_cast<const half*>(p.svh_ptrs[mat]);
-        A_raw += (size_t) slot * p.a_mat_stride; Cout += (size_t) slot * p.c_mat_stride;
+        A_raw += (size_t) slot * p.a_mat_stride;
+        if (p.rag) Cout = reinterpret_cast<char*>(p.c_ptrs[mat]); else Cout += (size_t) slot * p.c_mat_stride;
     }
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -186,7 +197,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     if (threadIdx.x == 0) stamp(1);
 
     const int KB = p.k / 128;
-    const int strips = p.n / 128;
+    const int strips = n_loc / 128;
     const long long U = (long long) KB * strips;
     const long long ubeg = unit_begin(U, G, cta), uend = unit_begin(U, G, cta + 1);
     const int n_units = (int) (uend - ubeg);
@@ -306,7 +317,10 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     {
         // =========================== producer ===========================
         const void* tm = tmap_w;
-        if (multi)
+        const bool rag = multi && p.rag;             // fan-out: widths differ, so no shared tensor map: eight row copies per unit
+        const uint8_t* wsrc = rag ? reinterpret_cast<const uint8_t*>(p.B_ptrs[mat]) : nullptr;
+        const size_t w_pitch = (size_t) (n_loc / 16) * 32 * K;               // bytes per 16-row tile row of the packed tensor
+        if (multi && !rag)
         {
             // per-CTA tensor map: the template (dims / strides / box of this shape) with matrix `mat`'s address
             uint8_t* stm = smem + ((L.off_bars + 640 + 127) & ~127);
@@ -316,7 +330,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
             tmap_patch_address(smem_u32(stm), gtm, p.B_ptrs[mat], lane);
             tm = gtm;
         }
-        else if (elect_one()) prefetch_tmap(tmap_w);
+        else if (!multi && elect_one()) prefetch_tmap(tmap_w);
         const uint64_t pol_w = policy_evict_first();
         const uint32_t w_smem0 = smem_u32(smem);
         int strip = (int) (ubeg / KB), kb = (int) (ubeg % KB);
@@ -324,7 +338,16 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
         for (int u = 0; u < n_units; ++u)
         {
             if (u >= S) { I8_WAITCNT(wf_a, W_EMPTY(s), ph ^ 1); mbar_wait<64>(W_EMPTY(s), ph ^ 1); }
-            if (elect_one())
+            if (rag)
+            {
+                // the unit's 8 tile rows x 256 K bytes, one bulk copy per row (lanes 0..7), landing exactly where the 2-D box would
+                if (lane == 0) mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
+                __syncwarp();
+                if (lane < 8)
+                    bulk_g2s(w_smem0 + s * L.w_bytes + lane * (256 * K), wsrc + (size_t) (kb * 8 + lane) * w_pitch + (size_t) strip * (256 * K),
+                             256 * K, W_FULL(s), pol_w);
+            }
+            else if (elect_one())
             {
                 mbar_arrive_expect_tx(W_FULL(s), (uint32_t) L.w_bytes);
                 tma_load_2d(w_smem0 + s * L.w_bytes, tm, strip * (32 * K), kb * 8, W_FULL(s), pol_w);
@@ -649,7 +672,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
             if constexpr (!AR)
             {
                 for (int r = q; r < p.m; r += 4)
-                    output_row_128(tile + r * 128, Cout, (size_t) r * p.n + strip * 128,
+                    output_row_128(tile + r * 128, Cout, (size_t) r * n_loc + strip * 128,
                                    svh ? svh + strip * 128 : nullptr, ROUTED ? routed_scale : p.out_scale, p.c_fp32 != 0, lane);
             }
             else
@@ -669,7 +692,7 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
                 {
                     float v[4];
                     finish_row_128_f32(tile + r * 128, svh ? svh + strip * 128 : nullptr, ROUTED ? routed_scale : p.out_scale, lane, v);
-                    const long long e0 = (long long) r * p.n + strip * 128 + lane * 4;
+                    const long long e0 = (long long) r * n_loc + strip * 128 + lane * 4;
                     uint4 mine = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
                     if (mine.x == I8_SENTINEL) mine.x = 0x7fc00000u;            // a NaN stays a NaN
                     if (mine.y == I8_SENTINEL) mine.y = 0x7fc00000u;

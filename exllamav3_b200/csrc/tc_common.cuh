@@ -15,6 +15,7 @@ constexpr int TC_DEC_WARPS = 16;             // 4 per lane quarter: tiles {h, h+
 constexpr int TC_DEC_GROUPS = 4;             // exact path: groups of 4 warps, each owning every 4th unit
 constexpr int TC_EPI_WARP0 = TC_DEC_WARP0 + TC_DEC_WARPS;
 constexpr int TC_MAX_STAGES = 16;
+constexpr int TC_RAG_MAX_MATS = 8;          // matrices of a fan-out launch (per-matrix widths)
 constexpr int TC_A_STAGE_COLS = 64;          // 128 k-values x fp16, 2 per 32-bit TMEM column
 
 struct TcParams
@@ -42,6 +43,13 @@ struct TcParams
     const uint64_t* B_ptrs; const uint64_t* suh_ptrs; const uint64_t* svh_ptrs;
     long long a_mat_stride;      // elements between the inputs of consecutive matrices (0 = shared input)
     long long c_mat_stride;      // bytes between the outputs of consecutive matrices
+    // fan-out (exl3_mgemm with per-matrix output widths, size_n_list / c_ptrs): matrix j is rag_n[j] columns wide, writes to
+    // c_ptrs[j] (device table) with row stride rag_n[j], and owns the CTAs rag_cta0[j] .. rag_cta0[j + 1] - 1 (proportional
+    // to its number of units).  rag == 0: uniform widths, fields unused.
+    int rag;
+    int rag_n[TC_RAG_MAX_MATS];
+    int rag_cta0[TC_RAG_MAX_MATS + 1];
+    const uint64_t* c_ptrs;
     float* parts;                // i8 path: sentinel-managed split-K exchange buffer (one 4 x 128 fp32 slot per CTA)
     uint8_t* tmap_slots;         // one 128-byte tensor-map slot per CTA (global memory)
     int knob_;                   // bring-up experiment switches (0 in production): 1 skip decode math, 2 skip STTM, 4 skip MMA

@@ -76,6 +76,8 @@ class _ChainPlan(ctypes.Structure):
     _fields_ = [("stages", _i), ("grid", _i), ("ring_stages", _i), ("smem_bytes", _i), ("cache_bytes", _i), ("units", _i64)]
 
 
+_lib.exl3b_register_widths.argtypes = [_vp, _vp, _i]; _lib.exl3b_register_widths.restype = _i
+_lib.exl3b_plan_fanout.argtypes = [_i, _vp, _i, _i, _vp]; _lib.exl3b_plan_fanout.restype = _i
 _lib.exl3b_chain_plan.argtypes = [ctypes.POINTER(_ChainOp), _i, _i, ctypes.POINTER(_ChainPlan)]; _lib.exl3b_chain_plan.restype = _i
 _lib.exl3b_chain_walk.argtypes = [ctypes.POINTER(_ChainOp), _i, _i, _i, _vp, _i]; _lib.exl3b_chain_walk.restype = _i
 _lib.exl3b_chain_create.argtypes = [ctypes.POINTER(_ChainOp), _i, ctypes.POINTER(_vp)]; _lib.exl3b_chain_create.restype = _i
@@ -355,6 +357,37 @@ def _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, 
     return tag
 
 
+# size_n_list tensors whose host copy the library knows: data_ptr -> (torch version counter, widths).  The copy to the host
+# synchronises, so it happens on the first call with a tensor (or after an in-place change of it) -- never during stream
+# capture: an unregistered list simply takes the generic path there.
+_widths_known: dict = {}
+
+
+def _register_widths(size_n_list) -> None:
+    key = size_n_list.data_ptr()
+    ver = size_n_list._version
+    hit = _widths_known.get(key)
+    if hit is not None and hit[0] == ver and hit[2] == size_n_list.numel():
+        return
+    if torch.cuda.is_current_stream_capturing():
+        if hit is not None:                       # stale entry: the library must not trust it
+            _lib.exl3b_register_widths(ctypes.c_void_p(key), None, 0)
+            del _widths_known[key]
+        return
+    widths = [int(v) for v in size_n_list.detach().cpu().tolist()]
+    arr = (ctypes.c_int32 * len(widths))(*widths)
+    _check(_lib.exl3b_register_widths(ctypes.c_void_p(key), arr, len(widths)))
+    _widths_known[key] = (ver, widths, size_n_list.numel())
+
+
+def plan_fanout(k: int, widths, num_sms: int):
+    """CTA-group boundaries of a fan-out launch (host logic, no GPU needed); None if the shapes are not eligible."""
+    arr = (ctypes.c_int32 * len(widths))(*[int(w) for w in widths])
+    out = (ctypes.c_int32 * (len(widths) + 1))()
+    g = _lib.exl3b_plan_fanout(int(k), arr, len(widths), int(num_sms), out)
+    return list(out) if g > 0 else None
+
+
 def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_idx: int, mcg, mul1,
                min_index: int, max_index: int, force_num_sms: int, num_tokens: int = 1,
                size_n_list=None, c_ptrs=None) -> int:
@@ -398,6 +431,8 @@ def exl3_mgemm(A, B, C, suh, A_had, svh, indices, weights, K: int, force_shape_i
         tag = _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, k, n, force_num_sms)
         if tag is not None:
             return tag
+    if size_n_list is not None:
+        _register_widths(size_n_list)
     with torch.cuda.device(A.device):
         return _check(_lib.exl3b_mgemm(
             _stream(A), _ptr(A), _ptr(B), _ptr(C), _ptr(suh), _ptr(A_had), _ptr(svh),

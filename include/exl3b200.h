@@ -146,6 +146,21 @@ int exl3b_mgemm(void* stream,
                 int force_shape_idx, int force_num_sms);
 
 /*
+ * Fan-out launches (exl3_mgemm with size_n_list / c_ptrs: several projections of the same input with different widths in one
+ * launch, as the reference's fused attention does, exllamav3_ext/libtorch/dsv4_attn.cpp:88-99).  The reference's operator hands
+ * over the widths as a DEVICE tensor only; the tensor-core path needs them on the host to lay out the launch (CTA groups
+ * proportional to the matrices' sizes, the packed tensors' row pitch).  A caller that keeps the list unchanged registers a host
+ * copy once:
+ *   exl3b_register_widths(size_n_list (device address, the key), host_widths, count)     count = 0 forgets the entry
+ * exl3b_mgemm then runs registered fan-outs (mul1, <= 4 rows, widths multiples of 128, <= 8 matrices, no indices) as ONE
+ * launch of the tcgen05 int8 kernel; unregistered lists, or shapes outside that envelope, take the generic path as before.
+ * The caller must re-register when it rewrites the device tensor (the shim in ext.py keys on torch's version counter).
+ * exl3b_plan_fanout: the CTA-group boundaries the launch would use (cta0[count + 1]); returns the grid size, 0 = not eligible.
+ */
+int exl3b_register_widths(const int32_t* size_n_list, const int32_t* host_widths, int count);
+int exl3b_plan_fanout(int k, const int32_t* host_widths, int count, int num_sms, int32_t* cta0);
+
+/*
  * ---- GEMM chains: one persistent launch for the quantized linears of a decode block ------------------------------------
  *
  * The reference runs the linears of a block as separate graph nodes of its C++ block modules: BC_GatedMLP issues

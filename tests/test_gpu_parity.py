@@ -176,6 +176,40 @@ def test_reconstruct_had(cuda, K, cb):
     assert torch.equal(w2.cpu(), w[:, 128:].cpu())
 
 
+@pytest.mark.parametrize("K,cb", [(1, 0), (2, 1), (3, 2), (4, 2), (5, 0), (6, 2), (7, 1), (8, 2)])
+def test_reconstruct_had_tensor_core_and_cuda_core_twins(cuda, K, cb):
+    # reconstruct_tc.cu (both Hadamards as tcgen05 GEMMs, the default) against the oracle and against the CUDA-core
+    # kernel of kernels_basic.cu on a shape with more blocks than one wave of the persistent grid covers per CTA
+    from exllamav3_b200 import ext
+    k, n = 1024, 5120 if K <= 4 else 2560
+    tr, suh, svh, _ = orc.make_synthetic(k, n, K, seed=K * 10 + cb)
+    outs = {}
+    try:
+        for mode in (1, 2, 21, 22, 24):              # CUDA cores; tensor cores: default, 1 / 2 / 4 threads per row
+            ext.lib.exl3b_debug_reconstruct_had(mode)
+            w = torch.full((k, n), float("nan"), dtype=torch.half, device=cuda)
+            ext.reconstruct_had_slice(w, T(tr, cuda), T(suh, cuda), T(svh, cuda), K, cb == 1, cb == 2, 0)
+            outs[mode] = w.cpu().numpy().astype(np.float64)
+            # column window of the packed tensor (modules/quant/exl3.py:199-211)
+            w2 = torch.empty((k, 384), dtype=torch.half, device=cuda)
+            ext.reconstruct_had_slice(w2, T(tr, cuda), T(suh, cuda), T(svh[256:640], cuda), K, cb == 1, cb == 2, 256)
+            assert torch.equal(w2.cpu(), w[:, 256:640].cpu())
+    finally:
+        ext.lib.exl3b_debug_reconstruct_had(0)
+    # oracle on the first 256 rows (the transform is block-diagonal over 128-row blocks)
+    ref = orc.get_weight_tensor_f64(tr[:16], suh[:256], svh, K, cb)
+    for mode in outs:
+        assert np.isfinite(outs[mode]).all()
+        assert np.abs(outs[mode][:256] - ref).max() / np.abs(ref).max() < 2e-3, mode
+    for mode in (21, 22, 24):
+        assert np.array_equal(outs[mode], outs[2]), mode        # the thread split does not change a single bit
+    # the two kernels round at the same places (fp16 tile between the passes, fp16 scale multiplies): they differ by
+    # the summation order inside the 128-term sums only, i.e. by a few fp16 ulps on few elements
+    d = np.abs(outs[1] - outs[2])
+    assert d.max() <= 4e-3 * np.abs(outs[1]).max()
+    assert (d > 0).mean() < 0.05
+
+
 def test_hgemm(cuda):
     from exllamav3_b200 import ext
     rng = np.random.default_rng(0)
