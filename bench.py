@@ -180,7 +180,7 @@ def run_reference_arm(args, cfg):
 class Token:
     """All quantized linears of one token for one TP rank, with their input/output/scratch buffers."""
 
-    def __init__(self, cfg, tp, rank, dev, seed=1234, fuse=True, mode="ops"):
+    def __init__(self, cfg, tp, rank, dev, seed=1234, fuse=True, mode="ops", fanout=True):
         import torch
         from exllamav3_b200 import ext
         self.ext, self.torch, self.dev, self.tp = ext, torch, dev, tp
@@ -211,25 +211,57 @@ class Token:
         # ext.exl3_gemv_int8_max_k(device) < K -- the reference's own extension answers 6 on Blackwell (its separate int8 GEMVs
         # beat its fused kernel), this library's shim answers 0 (the fused launch is the faster one here), so through the
         # drop-in boundary the model issues exactly this launch list.  --no-fuse times one launch per projection.
-        self.launches = []
+        #
+        # Fan-out (default; --no-fanout = the list above): q, k and v read the same input too, but q is wider than k / v.  The
+        # reference's exl3_mgemm takes per-matrix output widths for exactly this (size_n_list + c_ptrs, exl3_gemm.cu:402-447,
+        # exl3_gemm_kernel.cuh:172-181) and its fused attention issues its same-input projections that way
+        # (libtorch/dsv4_attn.cpp:88-99 "fan"); its Llama attention module does not (q_proj, then multi_kv: modules/attn.py:555-631).
+        # With fan-out the three projections are ONE operator call: 4 launches per layer instead of 5.  INTEGRATION.md shows the
+        # module-side change; the bench line carries the token time of BOTH launch lists.
+        self.fanout = bool(fanout and fuse)
+        self.launches = self._launch_list(fuse, self.fanout)
+        self.launches_ref = self._launch_list(fuse, False) if self.fanout else self.launches
+        self.alg_bytes = self.list_alg_bytes(self.launches)
+
+        if mode != "ops":
+            self.build_chains(mode)
+
+    def _launch_list(self, fuse, fanout):
+        torch, dev = self.torch, self.dev
+        out = []
         i = 0
         while i < len(self.mats):
             a = self.mats[i]
             b = self.mats[i + 1] if i + 1 < len(self.mats) else None
-            if fuse and b is not None and (a["name"], b["name"]) in (("k", "v"), ("gate", "up")) and a["layer"] == b["layer"]:
+            c = self.mats[i + 2] if i + 2 < len(self.mats) else None
+            if (fanout and c is not None and (a["name"], b["name"], c["name"]) == ("q", "k", "v") and a["layer"] == c["layer"]
+                    and a["k"] == b["k"] == c["k"] and a["K"] == b["K"] == c["K"] and a["y"].dtype == b["y"].dtype == c["y"].dtype):
+                grp = (a, b, c)
+                ptr = lambda key: torch.tensor([t[key].data_ptr() for t in grp], dtype=torch.long, device=dev)
+                out.append(dict(kind="mgemm", x=a["x"].view(1, 1, -1), K=a["K"], reduce=False, B=ptr("tr"), suh=ptr("suh"), svh=ptr("svh"),
+                                y=torch.empty((3, 1, max(t["n"] for t in grp)), dtype=a["y"].dtype, device=dev),     # dtype / max-width carrier
+                                xh=torch.empty((3, 1, a["k"]), dtype=torch.half, device=dev),
+                                snl=torch.tensor([t["n"] for t in grp], dtype=torch.int, device=dev), cp=ptr("y"), shared_inputs=3))
+                i += 3
+            elif fuse and b is not None and (a["name"], b["name"]) in (("k", "v"), ("gate", "up")) and a["layer"] == b["layer"]:
                 ptr = lambda key: torch.tensor([a[key].data_ptr(), b[key].data_ptr()], dtype=torch.long, device=dev)
                 y2 = torch.empty((2, 1, a["n"]), dtype=a["y"].dtype, device=dev)
                 xh2 = torch.empty((2, 1, a["k"]), dtype=torch.half, device=dev)
-                self.launches.append(dict(kind="mgemm", x=a["x"].view(1, 1, -1), y=y2, xh=xh2, K=a["K"], reduce=False,
-                                          B=ptr("tr"), suh=ptr("suh"), svh=ptr("svh")))
-                self.alg_bytes -= 2 * a["k"]            # the shared input is read once
+                out.append(dict(kind="mgemm", x=a["x"].view(1, 1, -1), y=y2, xh=xh2, K=a["K"], reduce=False,
+                                B=ptr("tr"), suh=ptr("suh"), svh=ptr("svh"), snl=None, cp=None, shared_inputs=2))
                 i += 2
             else:
-                self.launches.append(dict(kind="gemm", mt=a, reduce=a["reduce"]))
+                out.append(dict(kind="gemm", mt=a, reduce=a["reduce"]))
                 i += 1
+        return out
 
-        if mode != "ops":
-            self.build_chains(mode)
+    def list_alg_bytes(self, launches):
+        """Algorithmic bytes of a launch list: every matrix's own bytes, a shared input counted once."""
+        b = sum(alg_bytes(1, t["k"], t["n"], t["K"], t["c_fp32"]) for t in self.mats)
+        for ln in launches:
+            if ln["kind"] == "mgemm":
+                b -= 2 * ln["x"].shape[-1] * (ln["shared_inputs"] - 1)
+        return b
 
     def build_chains(self, mode):
         """
@@ -277,7 +309,7 @@ class Token:
             self.chain_items.append((ext.GemmChain([op(hd, x=hd["x"])]), None))
         self.launches = self.chain_items
 
-    def run(self):
+    def run(self, launches=None):
         ext, dist = self.ext, None
         if self.mode != "ops":
             for ch, red in self.chain_items:
@@ -286,7 +318,7 @@ class Token:
                     import torch.distributed as dist
                     dist.all_reduce(red["y"])
             return
-        for ln in self.launches:
+        for ln in (self.launches if launches is None else launches):
             if ln["kind"] == "gemm":
                 mt = ln["mt"]
                 if mt["reduce"] and self.fused_reduce:
@@ -298,7 +330,7 @@ class Token:
                     dist.all_reduce(mt["y"])
             else:
                 ext.exl3_mgemm(ln["x"], ln["B"], ln["y"], ln["suh"], ln["xh"], ln["svh"], None, None, ln["K"], -1,
-                               False, True, -1, -1, 0)
+                               False, True, -1, -1, 0, 1, ln["snl"], ln["cp"])
 
 
 def qgemm_section(tok, cfg, stream, hbm_peak):
@@ -488,7 +520,7 @@ def run_gpu_arm(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     from exllamav3_b200 import ext
 
-    tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse, mode=args.mode)
+    tok = Token(cfg, world if not args.tp_shapes else args.tp_shapes, rank, dev, fuse=not args.no_fuse, mode=args.mode, fanout=not args.no_fanout)
     if world > 1 and not args.nccl_allreduce and args.mode == "ops" and not args.tp_shapes:
         from exllamav3_b200 import tp as _tp
         try:
@@ -565,6 +597,29 @@ def run_gpu_arm(args, cfg):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
 
+    # ---- the same token with the reference's Llama launch list (q, k+v as two calls), same run, same weights ----
+    ref_list = None
+    if tok.fanout and args.mode == "ops" and tok.launches_ref is not tok.launches:
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                tok.run(tok.launches_ref)
+        stream.synchronize()
+        ref_fn = lambda: tok.run(tok.launches_ref)
+        if graph is not None:
+            try:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    tok.run(tok.launches_ref)
+                ref_fn = g2.replay
+            except Exception:
+                torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                ref_fn()
+        ref_ms = timed(ref_fn, args.steps) / args.steps
+        ref_list = {"launches": len(tok.launches_ref), "ms_per_step": ref_ms, "value": 1000.0 / ref_ms, "unit": "tok/s",
+                    "what": "q_proj and k+v (exl3_mgemm) as two operator calls per layer, as modules/attn.py:555-631 issues them"}
+
     # ---- end-to-end through the operator surface with host buffers ----
     hx = torch.randn((1, cfg["hidden"])).half().pin_memory()
     hlogits = torch.empty(tuple(tok.logits.shape), dtype=tok.logits.dtype).pin_memory()
@@ -634,8 +689,13 @@ def run_gpu_arm(args, cfg):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.model} EXL3 4.0bpw (lm_head 6bpw) b=1 decode: "
                                    f"{len(tok.mats)} quantized matrices/token in {len(tok.launches)} launches "
-                                   f"(k+v and gate+up as one exl3_mgemm each: what the reference's model code issues through this library's "
-                                   f"ext shim, model/config.py:48-64), m=1, mul1 codebook, "
+                                   + ("(q+k+v as one fan-out exl3_mgemm with per-matrix widths -- the operator's size_n_list / c_ptrs arguments, "
+                                      "exl3_gemm.cu:402-447, used like the reference's libtorch/dsv4_attn.cpp:88-99 -- and gate+up as one exl3_mgemm; "
+                                      "reference_launch_list = the same token with q and k+v as two calls, the reference's Llama module code), "
+                                      if tok.fanout and args.mode == "ops" else
+                                      "(k+v and gate+up as one exl3_mgemm each: what the reference's model code issues through this library's "
+                                      "ext shim, model/config.py:48-64), ") +
+                                   f"m=1, mul1 codebook, "
                                    f"random-init trellis",
                        "parallelism": (f"tp{world}" if world > 1 else "single") + (f" (DRY RUN of tp{args.tp_shapes} rank-0 shapes, no collective: not a result)" if args.tp_shapes else ""),
                        "l2": "weights per step (%.2f GB/rank) exceed L2 (126 MB); no flush needed" % (tok.alg_bytes / 1e9),
@@ -655,6 +715,7 @@ def run_gpu_arm(args, cfg):
                     "eager_value": (1000.0 / e2e_eager_ms) if e2e_eager_ms else None,
                     "note": "value: CUDA-graph replay of the token between the host copies; eager_value: the same with one "
                             "Python -> ctypes -> C-ABI call per launch (no graph), as the reference's eager module path issues them"},
+            "reference_launch_list": ref_list,
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "check": check,
@@ -682,6 +743,7 @@ def main():
     ap.add_argument("--mode", default="ops", choices=["ops", "blocks", "layer", "token"],
                     help="ops: one exl3_gemm / exl3_mgemm launch per projection group (the reference's eager operator granularity); "
                          "blocks / layer / token: GEMM chains (one persistent launch per block, per layer, per token)")
+    ap.add_argument("--no-fanout", action="store_true", help="q, k+v as two operator calls like the reference's Llama attention module (no q+k+v fan-out exl3_mgemm)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per projection (no exl3_mgemm for k+v / gate+up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qgemm", action="store_true", help="skip the per-shape qgemm GB/s + prefill tensor-pipe section (N = 1 only)")

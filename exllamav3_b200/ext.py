@@ -357,27 +357,41 @@ def _mgemm_split(A, B, C, suh, A_had, svh, K, cb, c_fp32, bszm_in, bszm_out, m, 
     return tag
 
 
-# size_n_list tensors whose host copy the library knows: data_ptr -> (torch version counter, widths).  The copy to the host
-# synchronises, so it happens on the first call with a tensor (or after an in-place change of it) -- never during stream
-# capture: an unregistered list simply takes the generic path there.
+# size_n_list tensors whose host copy the library knows: device address -> (weak reference to THE tensor object, torch version
+# counter, widths).  An entry is trusted only for the very tensor object it was made from (a freed tensor's address is reused by
+# the caching allocator, found the hard way) at the same version (in-place writes bump it); when that object dies the entry is
+# withdrawn from the library.  The copy to the host synchronises, so it happens on the first call with a tensor object -- never
+# during stream capture: an unknown list simply takes the generic path there.
 _widths_known: dict = {}
 
 
+def _forget_widths(key: int, ref) -> None:
+    hit = _widths_known.get(key)
+    if hit is not None and hit[0] is ref:
+        del _widths_known[key]
+        try:
+            _lib.exl3b_register_widths(ctypes.c_void_p(key), None, 0)
+        except Exception:                          # interpreter shutdown
+            pass
+
+
 def _register_widths(size_n_list) -> None:
+    import weakref
     key = size_n_list.data_ptr()
     ver = size_n_list._version
     hit = _widths_known.get(key)
-    if hit is not None and hit[0] == ver and hit[2] == size_n_list.numel():
+    if hit is not None and hit[0]() is size_n_list and hit[1] == ver:
         return
+    if hit is not None:                            # another tensor at this address, or rewritten: the library must not trust it
+        del _widths_known[key]
+        _lib.exl3b_register_widths(ctypes.c_void_p(key), None, 0)
     if torch.cuda.is_current_stream_capturing():
-        if hit is not None:                       # stale entry: the library must not trust it
-            _lib.exl3b_register_widths(ctypes.c_void_p(key), None, 0)
-            del _widths_known[key]
         return
     widths = [int(v) for v in size_n_list.detach().cpu().tolist()]
     arr = (ctypes.c_int32 * len(widths))(*widths)
     _check(_lib.exl3b_register_widths(ctypes.c_void_p(key), arr, len(widths)))
-    _widths_known[key] = (ver, widths, size_n_list.numel())
+    ref = weakref.ref(size_n_list, lambda r, key=key: _forget_widths(key, r))
+    _widths_known[key] = (ref, ver, widths)
 
 
 def plan_fanout(k: int, widths, num_sms: int):

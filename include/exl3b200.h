@@ -154,7 +154,9 @@ int exl3b_mgemm(void* stream,
  *   exl3b_register_widths(size_n_list (device address, the key), host_widths, count)     count = 0 forgets the entry
  * exl3b_mgemm then runs registered fan-outs (mul1, <= 4 rows, widths multiples of 128, <= 8 matrices, no indices) as ONE
  * launch of the tcgen05 int8 kernel; unregistered lists, or shapes outside that envelope, take the generic path as before.
- * The caller must re-register when it rewrites the device tensor (the shim in ext.py keys on torch's version counter).
+ * The entry is the caller's promise about the memory at that address: withdraw or renew it when the tensor is rewritten or
+ * freed (a recycled address would otherwise inherit the old widths; the shim in ext.py ties the entry to the tensor object and
+ * its version counter and withdraws it when the object dies).
  * exl3b_plan_fanout: the CTA-group boundaries the launch would use (cta0[count + 1]); returns the grid size, 0 = not eligible.
  */
 int exl3b_register_widths(const int32_t* size_n_list, const int32_t* host_widths, int count);

@@ -1,6 +1,7 @@
 """
 bench.py's host logic without a GPU: the per-rank launch list of a token (what the reference's model code issues through the
-operator surface: q, k+v as one exl3_mgemm, o, gate+up as one exl3_mgemm, down per layer, then lm_head),
+operator surface: q+k+v as one fan-out exl3_mgemm (or q, k+v like the reference's Llama module), o, gate+up as one exl3_mgemm, down
+per layer, then lm_head),
 the tensor-parallel shard shapes, the algorithmic byte count of the roofline, and the control flow of Token.run() for the
 NCCL and the fused row-parallel variants -- with a recording stand-in for the extension (no kernel runs here).
 """
@@ -29,8 +30,15 @@ class Recorder:
         self.calls.append(("gemm_ar", A.shape[-1], C.shape[-1]))
         return 211
 
-    def exl3_mgemm(self, A, B, C, suh, A_had, svh, indices, weights, K, fsi, mcg, mul1, mn, mx, fns):
-        assert indices is None and weights is None and B.numel() == 2 and C.shape[0] == 2 and mn == -1 and mx == -1
+    def exl3_mgemm(self, A, B, C, suh, A_had, svh, indices, weights, K, fsi, mcg, mul1, mn, mx, fns, num_tokens=1, size_n_list=None, c_ptrs=None):
+        assert indices is None and weights is None and mn == -1 and mx == -1 and num_tokens == 1
+        if size_n_list is not None:
+            # fan-out: per-matrix widths, outputs through c_ptrs, C carries dtype and the maximum width
+            assert B.numel() == c_ptrs.numel() == size_n_list.numel() == C.shape[0] and C.shape[-1] == int(size_n_list.max())
+            assert size_n_list.dtype == torch.int and c_ptrs.dtype == torch.long and A_had.shape[0] == B.numel()
+            self.calls.append(("fanout", A.shape[-1]) + tuple(int(v) for v in size_n_list))
+            return 210
+        assert B.numel() == 2 and C.shape[0] == 2 and c_ptrs is None
         self.calls.append(("mgemm", A.shape[-1], C.shape[-1]))
         return 210
 
@@ -41,9 +49,18 @@ def test_token_launch_list_and_run_control_flow(tp, monkeypatch):
     tok = bench.Token(TINY, tp, 0, dev)
     sh = lambda x: max(128, (x // tp) // 128 * 128) if tp > 1 else x
     assert len(tok.mats) == 7 * TINY["layers"] + 1
-    assert len(tok.launches) == 5 * TINY["layers"] + 1          # k+v and gate+up fused: 161 launches for the 32-layer model
-    per_layer = [("gemm", 256, sh(256)), ("mgemm", 256, sh(128)), ("gemm", sh(256), 256), ("mgemm", 256, sh(512)), ("gemm", sh(512), 256)]
+    # default: q+k+v as one fan-out exl3_mgemm, gate+up as one exl3_mgemm: 129 launches for the 32-layer model; the reference's
+    # Llama launch list (q, then k+v) stays available for the same-run comparison: 161 launches
+    assert len(tok.launches) == 4 * TINY["layers"] + 1 and len(tok.launches_ref) == 5 * TINY["layers"] + 1
+    ref_layer = [("gemm", 256, sh(256)), ("mgemm", 256, sh(128)), ("gemm", sh(256), 256), ("mgemm", 256, sh(512)), ("gemm", sh(512), 256)]
+    per_layer = [("fanout", 256, sh(256), sh(128), sh(128))] + ref_layer[2:]
     head = ("gemm", 256, sh(640) if tp > 1 else 640)
+    rec = Recorder(); tok.ext = rec; tok.skip_reduce = True
+    tok.run(tok.launches_ref)
+    assert rec.calls == ref_layer * TINY["layers"] + [head]
+    assert tok.list_alg_bytes(tok.launches_ref) - tok.alg_bytes == 2 * 256 * TINY["layers"]        # one more read of the shared input per layer
+    nofan = bench.Token(TINY, tp, 0, dev, fanout=False)
+    assert len(nofan.launches) == 5 * TINY["layers"] + 1 and nofan.launches_ref is nofan.launches
 
     # (1) kernels only (the single-GPU bench, or --tp-shapes): no collective
     rec = Recorder(); tok.ext = rec; tok.skip_reduce = True
@@ -64,7 +81,7 @@ def test_token_launch_list_and_run_control_flow(tp, monkeypatch):
         reduced.clear()
         rec = Recorder(); tok.ext = rec; tok.fused_reduce = True
         tok.run()
-        fused_layer = [c if i not in (2, 4) else ("gemm_ar",) + c[1:] for i, c in enumerate(per_layer)]
+        fused_layer = [c if i not in (1, 3) else ("gemm_ar",) + c[1:] for i, c in enumerate(per_layer)]
         assert rec.calls == fused_layer * TINY["layers"] + [head]
         assert reduced == []
 
