@@ -60,6 +60,9 @@ using namespace ptx;
 #ifndef EXL3B_I8_HALF_STAGE
 #define EXL3B_I8_HALF_STAGE 0
 #endif
+#ifndef EXL3B_I8_ROWCOPY
+#define EXL3B_I8_ROWCOPY 0
+#endif
 
 constexpr int I8_MAX_M = 8;                                    // rows per launch: kernel instantiated for MR = 4 and MR = 8 rows
 constexpr int I8_A_STAGE_COLS = 128;
@@ -317,20 +320,24 @@ __device__ __forceinline__ void gemm_tc_i8_body(const TcParams& p, const CUtenso
     {
         // =========================== producer ===========================
         const void* tm = tmap_w;
-        const bool rag = multi && p.rag;             // fan-out: widths differ, so no shared tensor map: eight row copies per unit
-        const uint8_t* wsrc = rag ? reinterpret_cast<const uint8_t*>(p.B_ptrs[mat]) : nullptr;
+        // EXL3B_I8_ROWCOPY (experiment, measured slower: profiles/r02_notes.md 5): weights as eight row copies per unit instead of one
+        // 2-D tensor-map box -- 1 = multi-matrix launches, 2 = every launch, 3 = fan-out launches only (their first version)
+        const bool rag = (multi && (EXL3B_I8_ROWCOPY == 1 || (EXL3B_I8_ROWCOPY == 3 && p.rag))) || EXL3B_I8_ROWCOPY == 2;
+        const uint8_t* wsrc = !rag ? nullptr : multi ? reinterpret_cast<const uint8_t*>(p.B_ptrs[mat]) : reinterpret_cast<const uint8_t*>(p.B);
         const size_t w_pitch = (size_t) (n_loc / 16) * 32 * K;               // bytes per 16-row tile row of the packed tensor
         if (multi && !rag)
         {
-            // per-CTA tensor map: the template (dims / strides / box of this shape) with matrix `mat`'s address
+            // per-CTA tensor map: the template (dims / strides / box of this shape) with matrix `mat`'s address -- and, in a fan-out
+            // launch, its own width (innermost extent in 8-byte elements, row pitch in bytes)
             uint8_t* stm = smem + ((L.off_bars + 640 + 127) & ~127);
             reinterpret_cast<uint32_t*>(stm)[lane] = reinterpret_cast<const uint32_t*>(tmap_w)[lane];
             __syncwarp();
             void* gtm = p.tmap_slots + (size_t) blockIdx.x * 128;
-            tmap_patch_address(smem_u32(stm), gtm, p.B_ptrs[mat], lane);
+            if (p.rag) tmap_patch_address_width(smem_u32(stm), gtm, p.B_ptrs[mat], (uint32_t) (w_pitch / 8), (uint64_t) w_pitch, lane);
+            else tmap_patch_address(smem_u32(stm), gtm, p.B_ptrs[mat], lane);
             tm = gtm;
         }
-        else if (!multi && elect_one()) prefetch_tmap(tmap_w);
+        else if (!multi && !rag && elect_one()) prefetch_tmap(tmap_w);
         const uint64_t pol_w = policy_evict_first();
         const uint32_t w_smem0 = smem_u32(smem);
         int strip = (int) (ubeg / KB), kb = (int) (ubeg % KB);

@@ -135,6 +135,23 @@ __device__ __forceinline__ void tmap_patch_address(uint32_t smem_tmap, void* gme
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(gmem_tmap) : "memory");
 }
 
+// The same for a matrix whose WIDTH differs from the template's: innermost extent (elements) and row pitch (bytes) too.
+// (global_stride takes the byte value as of CUDA 12.5; older assemblers wanted it >> 4.)
+__device__ __forceinline__ void tmap_patch_address_width(uint32_t smem_tmap, void* gmem_tmap, uint64_t new_addr, uint32_t dim0_elems,
+                                                         uint64_t pitch_bytes, int lane)
+{
+    if (lane == 0)
+    {
+        asm volatile("tensormap.replace.tile.global_address.shared::cta.b1024.b64 [%0], %1;" :: "r"(smem_tmap), "l"(new_addr) : "memory");
+        asm volatile("tensormap.replace.tile.global_dim.shared::cta.b1024.b32 [%0], 0, %1;" :: "r"(smem_tmap), "r"(dim0_elems) : "memory");
+        asm volatile("tensormap.replace.tile.global_stride.shared::cta.b1024.b64 [%0], 0, %1;" :: "r"(smem_tmap), "l"(pitch_bytes) : "memory");
+    }
+    __syncwarp();
+    asm volatile("tensormap.cp_fenceproxy.global.shared::cta.tensormap::generic.release.gpu.sync.aligned [%0], [%1], 128;"
+                 :: "l"(gmem_tmap), "r"(smem_tmap) : "memory");
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(gmem_tmap) : "memory");
+}
+
 // ---- relaxed gpu-scope accesses (flag-in-data exchange through L2) ------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p)
 {
