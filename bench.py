@@ -406,6 +406,36 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
             out["decode_batch"][f"{name}_m{m}"] = {"us_per_launch": round(best, 2), "GBps": round(b / best / 1e3, 1),
                                                     "frac_of_hbm_peak": round(b / best / 1e3 / hbm_peak, 3), "tag": int(tag[0])}
             del g
+    # the other two codebooks at batch 1 (default path: exact tcgen05 kernel): same bytes, different decode
+    out["decode_codebooks"] = {}
+    for name in ("q", "gate"):
+        mats = by_name[name]
+        for cbn, mcg in (("3inst", False), ("mcg", True)):
+            if name == "gate" and cbn == "mcg":
+                continue
+            tag = [0]
+            def runc():
+                for mt in mats:
+                    tag[0] = ext.exl3_gemm(mt["x"], mt["tr"], mt["y"], mt["suh"], mt["xh"], mt["svh"], -1, mcg, False, 0)
+            with torch.cuda.stream(stream):
+                runc()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                runc()
+            best = None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream); g.replay(); g.replay(); e1.record(stream)
+                e1.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / (2 * len(mats))
+                best = us if best is None else min(best, us)
+            mt0 = mats[0]
+            b = alg_bytes(1, mt0["k"], mt0["n"], mt0["K"], mt0["c_fp32"])
+            out["decode_codebooks"][f"{name}_{cbn}"] = {"us_per_launch": round(best, 2), "GBps": round(b / best / 1e3, 1),
+                                                        "frac_of_hbm_peak": round(b / best / 1e3 / hbm_peak, 3), "tag": int(tag[0])}
+            del g
     # the reference's own CUDA kernels (unmodified sources compiled for sm_100a, oracle/_ref) on this GPU in this run, its default
     # configuration, same shapes and method (graph replay over >= 512 MB of rotated weight copies): the bar the kernels are held to
     ref_so = os.path.join(ROOT, "oracle", "_ref", "exl3_ref_ext.so")
@@ -419,7 +449,7 @@ def qgemm_section(tok, cfg, stream, hbm_peak):
                 res = json.load(open(os.path.join(td, "ref_bench_int8.json")))
             out["reference_cuda"] = {"what": "unmodified reference kernels (exllamav3_ext, default settings: its int8 GEMV for mul1 at m <= 2, "
                                              "mma.sync kernels otherwise), same GPU, same run, outside every timed region",
-                                     "shapes": {f"{d['shape']} m={d['m']}": {"us": round(d["us"], 2), "GBps": round(d["gbps"], 1)} for d in res}}
+                                     "shapes": {(d["shape"] if " m=" in d["shape"] else f"{d['shape']} m={d['m']}"): {"us": round(d["us"], 2), "GBps": round(d["gbps"], 1)} for d in res}}
         except Exception as e:
             out["reference_cuda"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     else:

@@ -15,24 +15,30 @@ SHAPES = [("q/o", 4096, 4096, 4, 1), ("k/v", 4096, 1024, 4, 1), ("gate/up", 4096
           ("lm_head", 4096, 128256, 6, 1), ("q/o m=8", 4096, 4096, 4, 8), ("gate/up m=32", 4096, 14336, 4, 32),
           ("q/o K=2", 4096, 4096, 2, 1), ("q/o K=3", 4096, 4096, 3, 1), ("q/o K=6", 4096, 4096, 6, 1),
           ("gate/up m=128", 4096, 14336, 4, 128)]
+# the other two codebooks (same bytes, different decode): the 3INST default of older conversions and the MCG variant, batch 1
+CB_SHAPES = [("q/o 3inst", 4096, 4096, 4, 1, "3inst"), ("gate/up 3inst", 4096, 14336, 4, 1, "3inst"), ("q/o mcg", 4096, 4096, 4, 1, "mcg")]
 
 
 def main(mode):
     import torch
     global SHAPES
     if os.environ.get("REF_BENCH_SHAPES") == "decode":       # bench.py's same-run leg: the Llama decode shapes only
-        SHAPES = SHAPES[:7]
+        SHAPES = SHAPES[:7] + CB_SHAPES
+    else:
+        SHAPES = SHAPES + CB_SHAPES
     dev = torch.device("cuda:0")
     if mode == "ours":
         from exllamav3_b200 import ext as e
-        gemm = lambda A, B, C, su, Ah, sv: e.exl3_gemm(A, B, C, su, Ah, sv, -1, False, True, 0)
+        gemm_cb = lambda A, B, C, su, Ah, sv, mcg, mul1: e.exl3_gemm(A, B, C, su, Ah, sv, -1, mcg, mul1, 0)
     else:
         sys.path.insert(0, os.path.join(HERE, "_ref"))
         import exl3_ref_ext as r
-        gemm = lambda A, B, C, su, Ah, sv: r.exl3_gemm(A, B, C, su, Ah, sv, -1, False, True, 0)
+        gemm_cb = lambda A, B, C, su, Ah, sv, mcg, mul1: r.exl3_gemm(A, B, C, su, Ah, sv, -1, mcg, mul1, 0)
     res = []
     g = torch.Generator(device=dev); g.manual_seed(0)
-    for (name, k, n, K, m) in SHAPES:
+    for shp in SHAPES:
+        (name, k, n, K, m), cbn = shp[:5], (shp[5] if len(shp) > 5 else "mul1")
+        gemm = lambda A, B, C, su, Ah, sv, mcg=(cbn == "mcg"), mul1=(cbn == "mul1"): gemm_cb(A, B, C, su, Ah, sv, mcg, mul1)
         nbytes = k * n * K // 8
         copies = max(2, min(64, (512 << 20) // nbytes + 1))
         Bs = [torch.randint(0, 65536, (k // 16, n // 16, 16 * K), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
@@ -71,7 +77,7 @@ def main(mode):
             e1.record(); e1.synchronize()
         us = e0.elapsed_time(e1) * 1000 / iters
         alg = nbytes + 2 * m * k + 2 * m * n + 2 * (k + n)
-        res.append(dict(timing=mode_used, shape=name, k=k, n=n, K=K, m=m, us=us, gbps=alg / us / 1e3, tag=int(tag) if tag is not None else None))
+        res.append(dict(timing=mode_used, shape=name, k=k, n=n, K=K, m=m, codebook=cbn, us=us, gbps=alg / us / 1e3, tag=int(tag) if tag is not None else None))
         print(mode, res[-1], flush=True)
         del Bs
         torch.cuda.empty_cache()

@@ -137,7 +137,9 @@ def test_qgemm_section_control_flow(monkeypatch):
     q = out["decode_hbm"]["q"]
     assert (q["k"], q["n"], q["K"]) == (256, 256, 4) and q["us_per_launch"] > 0 and q["GBps"] > 0 and q["frac_of_hbm_peak"] >= 0
     # every shape: one warm-up pass + one captured pass over its layer instances; the batch-8 / 32 leg adds the same for q twice
-    assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"] + 2 * 2 * TINY["layers"]    # q and o share the shape
+    # (q and o share the shape); the codebook leg adds the same for q twice more (3INST, MCG)
+    assert calls.count(("gemm", 256, 256)) == 2 * 2 * TINY["layers"] + 2 * 2 * TINY["layers"] + 2 * 2 * TINY["layers"]
+    assert set(out["decode_codebooks"]) == {"q_3inst", "q_mcg", "gate_3inst"}
     assert set(out["decode_batch"]) == {"q_m8", "q_m32", "gate_m8", "gate_m32", "down_m8", "down_m32"}
     assert out["decode_batch"]["q_m8"]["tag"] == 210 and "reference_cuda" in out
     assert set(out["reconstruct"]) == {"reconstruct_256x256", "reconstruct_had_256x256", "reconstruct_256x512", "reconstruct_had_256x512"}
