@@ -210,6 +210,33 @@ def test_reconstruct_had_tensor_core_and_cuda_core_twins(cuda, K, cb):
     assert (d > 0).mean() < 0.05
 
 
+def test_reconstruct_had_vs_reference_cuda_golden_and_fp32_model(cuda):
+    """Both reconstruct_had kernels on the cases captured from the reference's own kernel: within the reference's tolerance of its
+    output (which adds in fp16), and equal to the fp32-sum model (oracle.reconstruct_had_fp32_model) up to the order of the fp32
+    additions: a few fp16 ulps on few elements."""
+    p = os.path.join(GOLDEN, "ref_gpu.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden/ref_gpu.npz not generated yet")
+    from exllamav3_b200 import ext
+    g = np.load(p)
+    try:
+        for mode in (1, 2):
+            ext.lib.exl3b_debug_reconstruct_had(mode)
+            for (K, cb, k, n, off, nout) in [(4, 2, 128, 384, 128, 256), (3, 0, 128, 256, 0, 256)]:
+                tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+                w = torch.empty((k, nout), dtype=torch.half, device=cuda)
+                ext.reconstruct_had_slice(w, T(tr, cuda), T(suh, cuda), T(svh[off:], cuda), K, cb == 1, cb == 2, off)
+                got = w.cpu().numpy()
+                gold = g[f"rechad_{K}_{cb}_{k}_{n}_{off}_{nout}"].astype(np.float64)
+                assert np.abs(got.astype(np.float64) - gold).max() <= 2.5e-3 * np.abs(gold).max(), (mode, K, cb)
+                model = orc.reconstruct_had_fp32_model(tr[:, off // 16:(off + nout) // 16], suh, svh[off:off + nout], K, cb)
+                same = (got.view(np.uint16) == model.view(np.uint16)).mean()
+                d = np.abs(got.astype(np.float64) - model.astype(np.float64)).max()
+                assert same >= 0.97 and d <= 2e-3 * np.abs(gold).max(), (mode, K, cb, same, d)
+    finally:
+        ext.lib.exl3b_debug_reconstruct_had(0)
+
+
 def test_hgemm(cuda):
     from exllamav3_b200 import ext
     rng = np.random.default_rng(0)

@@ -172,6 +172,27 @@ def test_oracle_reconstruct_bitexact_vs_reference_cuda():
         assert (ours.view(np.uint16) == g[f"rec_{K}_{cb}_{k}_{n}"].view(np.uint16)).all(), (K, cb)
 
 
+RECHAD_CASES = [(4, 2, 128, 384, 128, 256), (3, 0, 128, 256, 0, 256)]        # oracle/gen_golden_gpu.py: K, cb, k, n, column offset, columns
+
+
+def test_reconstruct_had_vs_reference_cuda_golden():
+    """The fused reconstruction as the reference's OWN kernel computed it on a B200: the fp64 restatement reproduces it within the
+    reference's test bound (its kernel adds in fp16), and the fp32-sum model the CUDA kernels of this repo follow is closer to fp64
+    than the reference's output is."""
+    g = _gpu_golden()
+    for (K, cb, k, n, off, nout) in RECHAD_CASES:
+        tr, suh, svh, _ = orc.make_synthetic(k, n, K)
+        gold = g[f"rechad_{K}_{cb}_{k}_{n}_{off}_{nout}"].astype(np.float64)
+        f64 = orc.get_weight_tensor_f64(tr, suh, svh, K, cb)[:, off:off + nout]
+        model = orc.reconstruct_had_fp32_model(tr[:, off // 16:(off + nout) // 16], suh, svh[off:off + nout], K, cb).astype(np.float64)
+        mx = np.abs(f64).max()
+        rms = lambda a: np.sqrt(((a - f64) ** 2).mean()) / np.sqrt((f64 ** 2).mean())
+        assert np.abs(gold - f64).max() <= 2e-3 * mx                      # tests/test_reconstruct_had.py:56-58
+        assert np.abs(model - f64).max() <= 1.2e-3 * mx
+        assert np.abs(model - gold).max() <= 2.5e-3 * mx
+        assert rms(model) < 0.6 * rms(gold) and rms(gold) < 1.2e-3
+
+
 def test_oracle_had_bitexact_vs_reference_cuda():
     g = _gpu_golden()
     for (dt, mode, scale) in gg.had_cases():
