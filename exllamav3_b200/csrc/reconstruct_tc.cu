@@ -1,9 +1,10 @@
 // reconstruct_had on the tensor cores:  W = diag(suh) . H128 . W_hat . H128 . diag(svh)  per 128 x 128 block, both 128-point
 // Hadamards as tcgen05 GEMMs against the +-1 matrix H128 (exact in fp16, fp32 accumulation) instead of 2 x 7 butterfly
-// stages on the CUDA cores (kernels_basic.cu: 128 fp32 registers per thread, two CTAs per SM, ~37 us for 4096 x 4096
-// where the bytes need ~7).  Replaces the reference's reconstruct_had_kernel (exllamav3_ext/quant/reconstruct.cu:159-306).
+// stages on the CUDA cores (kernels_basic.cu: 128 fp32 registers per thread, two CTAs per SM, 45 us for 4096 x 4096
+// where the bytes need ~7; this kernel: 25 us, profiles/r02_reconstruct_had_tc_splits.jsonl).  Replaces the reference's reconstruct_had_kernel (exllamav3_ext/quant/reconstruct.cu:159-306).
 //
-// Per block (one CTA of 128 threads, two CTAs per SM, persistent over the blocks):
+// Per block (one CTA of 128 x SPLIT threads -- SPLIT threads share a column / row, default 2 --, two CTAs per SM, persistent over
+// the blocks; the next block's packed words are fetched one block ahead):
 //   1. thread = one column n: decode its 128 k-values (8 tiles, decode16) and store them as the B operand W_hat^T [n][k]
 //      (K-major core-matrix layout) in shared memory
 //   2. MMA 1 (8 x UTCHMMA, M = N = 128):  D[k'][n] = sum_k H[k'][k] W_hat[k][n]         (A = H from shared memory)
