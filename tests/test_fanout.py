@@ -33,6 +33,26 @@ def test_fanout_partition_properties():
     assert ext.plan_fanout(4096, [0, 128], 148) is None
 
 
+def test_fanout_covers_every_tp_shard_of_the_bench_models():
+    """The q + k + v call of bench.py's token at every tensor-parallel degree the driver runs (1, 2, 4, 8), both models: eligible
+    for the one-launch path, every matrix served, no CTA group larger than its unit count."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    from exllamav3_b200 import ext
+    for name, cfg in bench.MODELS.items():
+        for tp in (1, 2, 4, 8):
+            layer, _ = bench.token_plan(cfg, tp)
+            spec = {nm: (k, n, K) for (nm, k, n, K, _, _) in layer}
+            (kq, nq, Kq), (kk, nk, Kk), (kv, nv, Kv) = spec["q"], spec["k"], spec["v"]
+            assert kq == kk == kv and Kq == Kk == Kv
+            b = ext.plan_fanout(kq, [nq, nk, nv], 148)
+            assert b is not None, (name, tp)
+            units = [(kq // 128) * (w // 128) for w in (nq, nk, nv)]
+            assert b[-1] == min(148, sum(units)) and all(1 <= b[j + 1] - b[j] <= units[j] for j in range(3)), (name, tp, b)
+
+
 def test_width_cache_is_tied_to_the_tensor_object(monkeypatch):
     """The shim's host copy of a size_n_list is trusted only for the tensor object it was read from, at the same version: a new
     tensor at a recycled address, or an in-place write, re-reads; a dead tensor's entry is withdrawn from the library."""
