@@ -122,7 +122,7 @@ def fan_call(ext, x3, ts, outs, K, snl=None):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("k,widths,K", [(4096, [4096, 1024, 1024], 4), (8192, [1024, 128, 128], 4), (4096, [2048, 512, 512], 6),
-                                        (512, [256, 128, 640, 128], 3)])
+                                        (512, [256, 128, 640, 128], 3), (4096, [1024, 256, 256], 4), (4096, [512, 128, 128], 4)])
 @pytest.mark.parametrize("m", [1, 4])
 def test_fanout_equals_separate_calls_and_oracle(cuda, k, widths, K, m):
     from exllamav3_b200 import ext
